@@ -1,0 +1,542 @@
+// Memory-bound network operators around the convolutions (NHWC fp32): input normalisation,
+// BatchNorm (+residual +ReLU) forward/backward, 3x3/2 max-pool, decoder glue
+// (nearest-upsample + concat + reflection pad, and its adjoint), activation backward with bias
+// reduction, global mean, Adam.  Each replaces the ATen op named in include/fusiondepth_b200.h.
+//
+// All kernels map threadIdx.x to the channel (fastest) dimension so every warp access is a
+// contiguous 128 B line; reductions over pixels accumulate in fp64 so the batch statistics match
+// the reference's two-pass CPU result to fp32 rounding.
+#include "common.cuh"
+#include "../../include/fusiondepth_b200.h"
+
+namespace {
+
+__device__ __forceinline__ float act_grad(float y, int act) {
+  // derivative expressed through the activation OUTPUT y
+  switch (act) {
+    case FD_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case FD_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;          // alpha = 1: exp(x) = y + 1
+    case FD_ACT_SIGMOID: return y * (1.f - y);
+    case FD_ACT_TANH: return 1.f - y * y;
+    default: return 1.f;
+  }
+}
+
+__global__ void prep_input_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW,
+                                  float mean, float stdv) {
+  // x [B,C,HW] -> y [B,HW,C]; one thread per output pixel, C is tiny (2..6)
+  const int b = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  for (int c = 0; c < C; ++c)
+    y[((long)b * HW + p) * C + c] = __fdiv_rn(__fadd_rn(x[((long)b * C + c) * HW + p], -mean), stdv);
+}
+
+// ---- activation backward + bias gradient ---------------------------------------------------
+// grid.x covers channel groups of 32, grid.y pixel chunks; block (32, 8)
+__global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                               float* __restrict__ dpre, float* __restrict__ dbias, long M, int C,
+                               int act) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C) {
+    for (long m = blockIdx.y * 8 + threadIdx.y; m < M; m += (long)gridDim.y * 8) {
+      long o = m * C + c;
+      float g = dy[o] * act_grad(y[o], act);
+      dpre[o] = g;
+      acc += g;
+    }
+  }
+  if (dbias == nullptr) return;
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(&dbias[c], s);
+  }
+}
+
+// ---- BatchNorm -------------------------------------------------------------------------------
+// pass 1: per-channel sum / sum of squares in fp64
+__global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict__ ws, long M, int C) {
+  __shared__ double red[2][8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0, ss = 0.0;
+  if (c < C) {
+    for (long m0 = (long)blockIdx.y * 8 + threadIdx.y; m0 < M; m0 += (long)gridDim.y * 8 * 16) {
+      float ps = 0.f, pss = 0.f;                    // short fp32 runs, folded into fp64
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        long m = m0 + (long)j * gridDim.y * 8;
+        if (m < M) {
+          float v = x[m * C + c];
+          ps += v;
+          pss = fmaf(v, v, pss);
+        }
+      }
+      s += (double)ps;
+      ss += (double)pss;
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = s;
+  red[1][threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += red[0][i][threadIdx.x]; b += red[1][i][threadIdx.x]; }
+    atomicAdd(&ws[c], a);
+    atomicAdd(&ws[C + c], b);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ ws, float* running_mean,
+                                   float* running_var, int training, float momentum, float eps,
+                                   float* save_mean, float* save_rstd, long M, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (training) {
+    double mean = ws[c] / (double)M;
+    double var = ws[C + c] / (double)M - mean * mean;
+    if (var < 0) var = 0;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + (double)momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + (double)momentum * unb);
+  } else {
+    save_mean[c] = running_mean[c];
+    save_rstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+  }
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                int relu, float* __restrict__ y, long M, int C) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= C) return;
+  const float mu = mean[c], rs = rstd[c], g = gamma[c], bt = beta[c];
+  for (long m = blockIdx.y * 8 + threadIdx.y; m < M; m += (long)gridDim.y * 8) {
+    long o = m * C + c;
+    float v = (x[o] - mu) * rs * g + bt;
+    if (res) v += res[o];
+    if (relu) v = fmaxf(v, 0.f);
+    y[o] = v;
+  }
+}
+
+// backward pass 1: sum g, sum g*xhat with g = dy * relu_mask
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                     const float* __restrict__ dy, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, int relu,
+                                     double* __restrict__ ws, long M, int C) {
+  __shared__ double red[2][8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0, ss = 0.0;
+  if (c < C) {
+    const float mu = mean[c], rs = rstd[c];
+    for (long m0 = (long)blockIdx.y * 8 + threadIdx.y; m0 < M; m0 += (long)gridDim.y * 8 * 16) {
+      float ps = 0.f, pss = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        long m = m0 + (long)j * gridDim.y * 8;
+        if (m < M) {
+          long o = m * C + c;
+          float g = dy[o];
+          if (relu && !(y[o] > 0.f)) g = 0.f;
+          ps += g;
+          pss = fmaf(g, (x[o] - mu) * rs, pss);
+        }
+      }
+      s += (double)ps;
+      ss += (double)pss;
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = s;
+  red[1][threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += red[0][i][threadIdx.x]; b += red[1][i][threadIdx.x]; }
+    atomicAdd(&ws[c], a);
+    atomicAdd(&ws[C + c], b);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                    const float* __restrict__ dy, const float* __restrict__ gamma,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    int relu, int training, const double* __restrict__ ws,
+                                    float* __restrict__ dx, float* __restrict__ dres,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long M,
+                                    int C) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= C) return;
+  const float mu = mean[c], rs = rstd[c], gm = gamma[c];
+  const float sg = (float)ws[c], sgx = (float)ws[C + c];
+  const float k1 = training ? sg / (float)M : 0.f, k2 = training ? sgx / (float)M : 0.f;
+  if (blockIdx.y == 0 && threadIdx.y == 0) {
+    if (dgamma) dgamma[c] = sgx;
+    if (dbeta) dbeta[c] = sg;
+  }
+  for (long m = blockIdx.y * 8 + threadIdx.y; m < M; m += (long)gridDim.y * 8) {
+    long o = m * C + c;
+    float g = dy[o];
+    if (relu && !(y[o] > 0.f)) g = 0.f;
+    if (dres) dres[o] = g;
+    float xh = (x[o] - mu) * rs;
+    dx[o] = gm * rs * (g - k1 - xh * k2);
+  }
+}
+
+// ---- max-pool 3x3 stride 2 pad 1 -------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                   unsigned char* __restrict__ idx, int H, int W, int C, int Ho,
+                                   int Wo) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.z;
+  if (c >= C) return;
+  for (int p = blockIdx.y * blockDim.y + threadIdx.y; p < Ho * Wo; p += gridDim.y * blockDim.y) {
+    int ho = p / Wo, wo = p % Wo;
+    float best = -INFINITY;
+    int bi = 0;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int h = 2 * ho - 1 + kh, w = 2 * wo - 1 + kw;
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          float v = x[(((long)b * H + h) * W + w) * C + c];
+          if (v > best || v != v) { best = v; bi = kh * 3 + kw; }
+        }
+      }
+    long o = (((long)b * Ho + ho) * Wo + wo) * C + c;
+    y[o] = best;
+    idx[o] = (unsigned char)bi;
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx,
+                                   float* __restrict__ dx, int H, int W, int C, int Ho, int Wo) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.z;
+  if (c >= C) return;
+  for (int p = blockIdx.y * blockDim.y + threadIdx.y; p < H * W; p += gridDim.y * blockDim.y) {
+    int h = p / W, w = p % W;
+    float acc = 0.f;
+    // windows (ho,wo) containing (h,w): 2ho-1 <= h <= 2ho+1
+    for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho >= Ho) continue;
+      int kh = h - (2 * ho - 1);
+      for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo >= Wo) continue;
+        int kw = w - (2 * wo - 1);
+        long o = (((long)b * Ho + ho) * Wo + wo) * C + c;
+        if (idx[o] == kh * 3 + kw) acc += dy[o];
+      }
+    }
+    dx[(((long)b * H + h) * W + w) * C + c] = acc;
+  }
+}
+
+// ---- decoder glue ----------------------------------------------------------------------------
+constexpr int MAXSEG = 4;
+struct AsmArgs {
+  const float* a[MAXSEG];
+  const float* b[MAXSEG];
+  float* d[MAXSEG];
+  int C[MAXSEG], up[MAXSEG], off[MAXSEG];
+  int nseg, Ctot, B, H, W, pad;
+};
+
+__device__ __forceinline__ int refl(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__global__ void assemble_fwd_kernel(AsmArgs a, float* __restrict__ out) {
+  const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
+  const long npix = (long)a.B * Hp * Wp;
+  for (long p = blockIdx.x; p < npix; p += gridDim.x) {
+    int wp = p % Wp, hp = (p / Wp) % Hp, b = p / ((long)Wp * Hp);
+    int h = refl(hp - a.pad, a.H), w = refl(wp - a.pad, a.W);
+    float* o = out + p * a.Ctot;
+    for (int c = threadIdx.x; c < a.Ctot; c += blockDim.x) {
+      int s = 0;
+#pragma unroll
+      for (int i = 1; i < MAXSEG; ++i)
+        if (i < a.nseg && c >= a.off[i]) s = i;
+      int cs = c - a.off[s];
+      int hs = a.up[s] ? h >> 1 : h, ws = a.up[s] ? w >> 1 : w;
+      int Hs = a.up[s] ? a.H >> 1 : a.H, Ws = a.up[s] ? a.W >> 1 : a.W;
+      long i = (((long)b * Hs + hs) * Ws + ws) * a.C[s] + cs;
+      float v = a.a[s][i];
+      if (a.b[s]) v += a.b[s][i];
+      o[c] = v;
+    }
+  }
+}
+
+// adjoint, gather form: every source element sums the padded positions that read it
+__global__ void assemble_bwd_kernel(AsmArgs a, const float* __restrict__ dout, int s) {
+  const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
+  const int u = a.up[s] ? 2 : 1;
+  const int Hs = a.H / u, Ws = a.W / u, Cs = a.C[s];
+  const long npix = (long)a.B * Hs * Ws;
+  for (long p = blockIdx.x; p < npix; p += gridDim.x) {
+    int ws = p % Ws, hs = (p / Ws) % Hs, b = p / ((long)Ws * Hs);
+    for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+      float acc = 0.f;
+      for (int dy = 0; dy < u; ++dy) {
+        int h = hs * u + dy;
+        int hps[3], nh = 0;
+        hps[nh++] = h + a.pad;
+        if (a.pad) { if (h == 1) hps[nh++] = 0; if (h == a.H - 2) hps[nh++] = Hp - 1; }
+        for (int dx = 0; dx < u; ++dx) {
+          int w = ws * u + dx;
+          int wps[3], nw = 0;
+          wps[nw++] = w + a.pad;
+          if (a.pad) { if (w == 1) wps[nw++] = 0; if (w == a.W - 2) wps[nw++] = Wp - 1; }
+          for (int i = 0; i < nh; ++i)
+            for (int j = 0; j < nw; ++j)
+              acc += dout[(((long)b * Hp + hps[i]) * Wp + wps[j]) * a.Ctot + a.off[s] + c];
+        }
+      }
+      a.d[s][p * Cs + c] = acc;
+    }
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                           float* __restrict__ o, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    o[i] = a[i] + b[i];
+}
+
+__global__ void mean_hw_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C,
+                                   float scale) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int p = 0; p < HW; ++p) acc += x[((long)b * HW + p) * C + c];
+  y[b * C + c] = scale * (acc / (float)HW);
+}
+__global__ void mean_hw_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int HW, int C,
+                                   float scale) {
+  const int b = blockIdx.y;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)HW * C;
+       i += (long)gridDim.x * blockDim.x)
+    dx[(long)b * HW * C + i] = dy[b * C + (i % C)] * (scale / (float)HW);
+}
+
+__global__ void weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout,
+                                        int taps, int Cin) {
+  // w [Cout][taps][Cin] -> wt [Cin][taps][Cout]
+  long n = (long)Cout * taps * Cin;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int co = i % Cout;
+    int tp = (i / Cout) % taps;
+    int ci = i / ((long)Cout * taps);
+    wt[i] = w[((long)co * taps + tp) * Cin + ci];
+  }
+}
+
+// state[0] = step (int bits), state[1] = lr / (1 - beta1^t), state[2] = sqrt(1 - beta2^t);
+// kept on the device so a captured CUDA graph advances the step on every replay
+__global__ void adam_scalars_kernel(int* state, float lr, float beta1, float beta2) {
+  int t = state[0] + 1;
+  state[0] = t;
+  double bc1 = 1.0 - pow((double)beta1, (double)t);
+  double bc2 = 1.0 - pow((double)beta2, (double)t);
+  ((float*)state)[1] = (float)((double)lr / bc1);
+  ((float*)state)[2] = (float)sqrt(bc2);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long n, const int* __restrict__ state, float beta1,
+                            float beta2, float eps, float grad_scale) {
+  const float step_size = ((const float*)state)[1], bc2_sqrt = ((const float*)state)[2];
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float mi = m[i] * beta1 + gi * (1.f - beta1);
+    float vi = v[i] * beta2 + gi * gi * (1.f - beta2);
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+inline int pix_chunks(long M) {
+  long c = (M + 8 * 64 - 1) / (8 * 64);
+  if (c < 1) c = 1;
+  if (c > 592) c = 592;          // 4 waves of 148 SMs
+  return (int)c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fd_prep_input(const float* x, float* y, int B, int C, int H, int W, float mean, float stdv,
+                  void* stream) {
+  prep_input_kernel<<<dim3(fd::cdiv((long)H * W, 256), B), 256, 0, (cudaStream_t)stream>>>(
+      x, y, C, H * W, mean, stdv);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long M, int C, int act,
+               void* stream) {
+  act_bwd_kernel<<<dim3(fd::cdiv(C, 32), pix_chunks(M)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      y, dy, dpre, dbias, M, C, act);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
+              float* running_mean, float* running_var, int training, float momentum, float eps,
+              int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
+              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(fd::cdiv(C, 32), pix_chunks(M)), blk(32, 8);
+  if (training) {
+    cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
+    bn_stats_kernel<<<grid, blk, 0, st>>>(x, ws, M, C);
+    FD_CHECK_LAUNCH();
+  }
+  bn_finalize_kernel<<<fd::cdiv(C, 128), 128, 0, st>>>(ws, running_mean, running_var, training,
+                                                       momentum, eps, save_mean, save_rstd, M, C);
+  FD_CHECK_LAUNCH();
+  bn_apply_kernel<<<grid, blk, 0, st>>>(x, residual, gamma, beta, save_mean, save_rstd, relu, y, M, C);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
+              const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
+              float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
+              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(fd::cdiv(C, 32), pix_chunks(M)), blk(32, 8);
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
+  bn_bwd_reduce_kernel<<<grid, blk, 0, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
+  FD_CHECK_LAUNCH();
+  bn_bwd_apply_kernel<<<grid, blk, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training, ws,
+                                            dx, dresidual, dgamma, dbeta, M, C);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C,
+                        void* stream) {
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  dim3 grid(fd::cdiv(C, 32), min(fd::cdiv((long)Ho * Wo, 8), 1024), B);
+  maxpool_fwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, y, idx, H, W, C, Ho, Wo);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+int fd_maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, float* dx, int B, int H, int W,
+                        int C, void* stream) {
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  dim3 grid(fd::cdiv(C, 32), min(fd::cdiv((long)H * W, 8), 1024), B);
+  maxpool_bwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, idx, dx, H, W, C, Ho, Wo);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+static int fill_asm(AsmArgs& a, int nseg, const int* C, const int* up, int B, int H, int W, int pad) {
+  FD_REQUIRE(nseg >= 1 && nseg <= MAXSEG, "fd_assemble: 1..%d segments supported", MAXSEG);
+  FD_REQUIRE(pad == 0 || pad == 1, "fd_assemble: pad must be 0 or 1");
+  a.nseg = nseg; a.B = B; a.H = H; a.W = W; a.pad = pad;
+  int off = 0;
+  for (int i = 0; i < MAXSEG; ++i) {
+    a.a[i] = a.b[i] = nullptr; a.d[i] = nullptr;
+    a.C[i] = i < nseg ? C[i] : 0;
+    a.up[i] = i < nseg ? up[i] : 0;
+    a.off[i] = off;
+    off += a.C[i];
+    if (i < nseg && up[i]) FD_REQUIRE(H % 2 == 0 && W % 2 == 0, "fd_assemble: odd size with upsample");
+  }
+  a.Ctot = off;
+  return 0;
+}
+
+int fd_assemble_fwd(const fd_segment* segs, int nseg, float* out, int B, int H, int W, int pad,
+                    void* stream) {
+  AsmArgs a;
+  int C[MAXSEG], up[MAXSEG];
+  for (int i = 0; i < nseg && i < MAXSEG; ++i) { C[i] = segs[i].C; up[i] = segs[i].up; }
+  int rc = fill_asm(a, nseg, C, up, B, H, W, pad);
+  if (rc) return rc;
+  for (int i = 0; i < nseg; ++i) { a.a[i] = segs[i].a; a.b[i] = segs[i].b; }
+  long npix = (long)B * (H + 2 * pad) * (W + 2 * pad);
+  int threads = a.Ctot >= 256 ? 256 : (a.Ctot >= 128 ? 128 : (a.Ctot >= 64 ? 64 : 32));
+  long blocks = npix < 148L * 32 ? npix : 148L * 32;
+  assemble_fwd_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(a, out);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_assemble_bwd(const float* dout, float* const* dsegs, const int* C, const int* up, int nseg,
+                    int B, int H, int W, int pad, void* stream) {
+  AsmArgs a;
+  int rc = fill_asm(a, nseg, C, up, B, H, W, pad);
+  if (rc) return rc;
+  for (int s = 0; s < nseg; ++s) {
+    if (!dsegs[s]) continue;
+    a.d[s] = dsegs[s];
+    int u = up[s] ? 2 : 1;
+    long npix = (long)B * (H / u) * (W / u);
+    int threads = C[s] >= 256 ? 256 : (C[s] >= 128 ? 128 : (C[s] >= 64 ? 64 : 32));
+    long blocks = npix < 148L * 32 ? npix : 148L * 32;
+    assemble_bwd_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(a, dout, s);
+    FD_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+int fd_add(const float* a, const float* b, float* out, long n, void* stream) {
+  add_kernel<<<min(fd::cdiv(n, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_mean_hw_fwd(const float* x, float* y, int B, int HW, int C, float scale, void* stream) {
+  mean_hw_fwd_kernel<<<dim3(fd::cdiv(C, 64), B), 64, 0, (cudaStream_t)stream>>>(x, y, HW, C, scale);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+int fd_mean_hw_bwd(const float* dy, float* dx, int B, int HW, int C, float scale, void* stream) {
+  mean_hw_bwd_kernel<<<dim3(min(fd::cdiv((long)HW * C, 256), 1024), B), 256, 0, (cudaStream_t)stream>>>(
+      dy, dx, HW, C, scale);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_weight_transpose(const float* w, float* wt, int Cout, int taps, int Cin, void* stream) {
+  long n = (long)Cout * taps * Cin;
+  weight_transpose_kernel<<<min(fd::cdiv(n, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, wt, Cout,
+                                                                                          taps, Cin);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                 float beta2, float eps, int* state, float grad_scale, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_scalars_kernel<<<1, 1, 0, st>>>(state, lr, beta1, beta2);
+  FD_CHECK_LAUNCH();
+  adam_kernel<<<min(fd::cdiv(n, 256), 148 * 16), 256, 0, st>>>(p, g, m, v, n, state, beta1, beta2, eps,
+                                                              grad_scale);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

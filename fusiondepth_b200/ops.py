@@ -1,0 +1,424 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels.
+
+PyTorch here is plumbing only: it owns device memory (torch.empty), the stream and the autograd
+tape.  Activations are fp32 tensors of logical shape [B,C,H,W] stored channels-last (NHWC); conv
+weights are logical [Cout,Cin,KH,KW] stored channels-last ([Cout,KH,KW,Cin]).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int, c_void_p
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+ACT = {"none": 0, "relu": 1, "elu": 2, "sigmoid": 3, "tanh": 4}
+CL = torch.channels_last
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, who: str):
+    if not t.is_cuda:
+        raise _lib.FusionDepthLibraryError(
+            "%s: fusiondepth_b200 operators run on CUDA only (got a %s tensor); there is no CPU "
+            "fallback" % (who, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s: expected float32, got %s" % (who, t.dtype))
+
+
+def nhwc(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous(memory_format=CL)
+
+
+def empty_nhwc(B, C, H, W, device):
+    return torch.empty((B, C, H, W), device=device, dtype=torch.float32, memory_format=CL)
+
+
+# --------------------------------------------------------------------------------------------
+class PrepInput(torch.autograd.Function):
+    """(x - 0.45)/0.225 and NCHW -> NHWC (resnet_encoder.py:94).  Inputs carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, "prep_input")
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        y = empty_nhwc(B, C, H, W, x.device)
+        _lib.check(_lib.load().fd_prep_input(_p(x), _p(y), B, C, H, W, 0.45, 0.225, _stream()),
+                   "fd_prep_input")
+        ctx.mark_non_differentiable(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return None
+
+
+def prep_input(x):
+    return PrepInput.apply(x)
+
+
+# --------------------------------------------------------------------------------------------
+class Conv2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act):
+        _require_cuda(x, "conv2d")
+        lib = _lib.load()
+        x = nhwc(x)
+        w = nhwc(weight)
+        B, Cin, H, W = x.shape
+        Cout, Cin_w, KH, KW = w.shape
+        if Cin_w != Cin:
+            raise RuntimeError("conv2d: input has %d channels, weight expects %d" % (Cin, Cin_w))
+        Ho = (H + 2 * pad - KH) // stride + 1
+        Wo = (W + 2 * pad - KW) // stride + 1
+        y = empty_nhwc(B, Cout, Ho, Wo, x.device)
+        _lib.check(lib.fd_conv2d_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, Cout, KH, KW,
+                                     stride, pad, act, _stream()), "fd_conv2d_fwd")
+        ctx.save_for_backward(x, w, y if act != 0 else None)
+        ctx.cfg = (stride, pad, act, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, w, y = ctx.saved_tensors
+        stride, pad, act, has_bias = ctx.cfg
+        B, Cin, H, W = x.shape
+        Cout, _, KH, KW = w.shape
+        dy = nhwc(dy)
+        M = dy.shape[0] * dy.shape[2] * dy.shape[3]
+        st = _stream()
+        dbias = None
+        if act != 0 or has_bias:
+            dbias = torch.zeros(Cout, device=x.device, dtype=torch.float32) if has_bias else None
+            dpre = torch.empty_like(dy) if act != 0 else dy
+            _lib.check(lib.fd_act_bwd(_p(y if act != 0 else dy), _p(dy), _p(dpre), _p(dbias), M, Cout,
+                                      act, st), "fd_act_bwd")
+            dy = dpre
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wt = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
+            _lib.check(lib.fd_weight_transpose(_p(w), _p(wt), Cout, KH * KW, Cin, st),
+                       "fd_weight_transpose")
+            dx = empty_nhwc(B, Cin, H, W, x.device)
+            _lib.check(lib.fd_conv2d_dgrad(_p(dy), _p(wt), _p(dx), B, H, W, Cin, Cout, KH, KW, stride,
+                                           pad, st), "fd_conv2d_dgrad")
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32,
+                             memory_format=CL)
+            _lib.check(lib.fd_conv2d_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW, stride,
+                                           pad, st), "fd_conv2d_wgrad")
+        return dx, dw, dbias, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, pad=0, act="none"):
+    return Conv2dFn.apply(x, weight, bias, int(stride), int(pad), ACT[act])
+
+
+# --------------------------------------------------------------------------------------------
+class BatchNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps,
+                relu):
+        _require_cuda(x, "batch_norm")
+        lib = _lib.load()
+        x = nhwc(x)
+        if residual is not None:
+            residual = nhwc(residual)
+        B, C, H, W = x.shape
+        M = B * H * W
+        y = torch.empty_like(x)
+        mean = torch.empty(C, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(C, device=x.device, dtype=torch.float32)
+        ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        _lib.check(lib.fd_bn_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(running_mean),
+                                 _p(running_var), int(training), momentum, eps, int(relu), _p(y),
+                                 _p(mean), _p(rstd), _p(ws), M, C, _stream()), "fd_bn_fwd")
+        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        ctx.cfg = (int(relu), int(training), residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        relu, training, has_res = ctx.cfg
+        dy = nhwc(dy)
+        B, C, H, W = x.shape
+        M = B * H * W
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
+        ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        _lib.check(lib.fd_bn_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(mean), _p(rstd), relu, training,
+                                 _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, _stream()),
+                   "fd_bn_bwd")
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, running_mean, running_var, residual=None, training=True,
+               momentum=0.1, eps=1e-5, relu=False):
+    return BatchNormFn.apply(x, gamma, beta, running_mean, running_var, residual, bool(training),
+                             float(momentum), float(eps), bool(relu))
+
+
+# --------------------------------------------------------------------------------------------
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, "maxpool3x3s2")
+        x = nhwc(x)
+        B, C, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = empty_nhwc(B, C, Ho, Wo, x.device)
+        idx = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+        _lib.check(_lib.load().fd_maxpool3x3s2_fwd(_p(x), _p(y), _p(idx), B, H, W, C, _stream()),
+                   "fd_maxpool3x3s2_fwd")
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        dy = nhwc(dy)
+        dx = empty_nhwc(B, C, H, W, dy.device)
+        _lib.check(_lib.load().fd_maxpool3x3s2_bwd(_p(dy), _p(idx), _p(dx), B, H, W, C, _stream()),
+                   "fd_maxpool3x3s2_bwd")
+        return dx
+
+
+def maxpool3x3s2(x):
+    return MaxPoolFn.apply(x)
+
+
+# --------------------------------------------------------------------------------------------
+class AssembleFn(torch.autograd.Function):
+    """out = reflect_pad(cat([seg_i])) with seg_i = (a_i [+ b_i]) optionally nearest-upsampled x2."""
+
+    @staticmethod
+    def forward(ctx, pad, spec, *tensors):
+        # spec: tuple of (has_b, up) per segment; tensors: a0,[b0],a1,[b1],...
+        lib = _lib.load()
+        segs = (_lib.Segment * len(spec))()
+        keep, it, Cs = [], iter(tensors), []
+        H = W = None
+        for i, (has_b, up) in enumerate(spec):
+            a = nhwc(next(it))
+            _require_cuda(a, "assemble")
+            b = nhwc(next(it)) if has_b else None
+            if b is not None and b.shape != a.shape:
+                raise RuntimeError("assemble: addend shape mismatch %s vs %s" % (a.shape, b.shape))
+            h, w = a.shape[2] * (2 if up else 1), a.shape[3] * (2 if up else 1)
+            if H is None:
+                H, W = h, w
+            elif (H, W) != (h, w):
+                raise RuntimeError("assemble: segment %d is %dx%d, expected %dx%d" % (i, h, w, H, W))
+            segs[i].a, segs[i].b = a.data_ptr(), (b.data_ptr() if b is not None else None)
+            segs[i].C, segs[i].up = a.shape[1], int(up)
+            Cs.append(a.shape[1])
+            keep += [a, b]
+        B = keep[0].shape[0]
+        out = empty_nhwc(B, sum(Cs), H + 2 * pad, W + 2 * pad, keep[0].device)
+        _lib.check(lib.fd_assemble_fwd(segs, len(spec), _p(out), B, H, W, pad, _stream()),
+                   "fd_assemble_fwd")
+        ctx.cfg = (pad, spec, Cs, B, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        pad, spec, Cs, B, H, W = ctx.cfg
+        dout = nhwc(dout)
+        n = len(spec)
+        ptrs = (c_void_p * n)()
+        Carr = (c_int * n)(*Cs)
+        uarr = (c_int * n)(*[int(u) for _, u in spec])
+        grads: List[Optional[torch.Tensor]] = []
+        need = ctx.needs_input_grad[2:]
+        k = 0
+        dsegs = []
+        for i, (has_b, up) in enumerate(spec):
+            wants = need[k] or (has_b and need[k + 1])
+            u = 2 if up else 1
+            d = empty_nhwc(B, Cs[i], H // u, W // u, dout.device) if wants else None
+            ptrs[i] = d.data_ptr() if d is not None else None
+            dsegs.append(d)
+            k += 2 if has_b else 1
+        _lib.check(lib.fd_assemble_bwd(_p(dout), ptrs, Carr, uarr, n, B, H, W, pad, _stream()),
+                   "fd_assemble_bwd")
+        k = 0
+        for i, (has_b, up) in enumerate(spec):
+            grads.append(dsegs[i] if need[k] else None)
+            if has_b:
+                grads.append(dsegs[i] if need[k + 1] else None)
+            k += 2 if has_b else 1
+        return (None, None) + tuple(grads)
+
+
+def assemble(segments: Sequence, pad: int = 1):
+    """segments: sequence of (a, b_or_None, upsample_bool)."""
+    spec, flat = [], []
+    for a, b, up in segments:
+        spec.append((b is not None, bool(up)))
+        flat.append(a)
+        if b is not None:
+            flat.append(b)
+    return AssembleFn.apply(int(pad), tuple(spec), *flat)
+
+
+# --------------------------------------------------------------------------------------------
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, "add")
+        a, b = nhwc(a), nhwc(b)
+        out = torch.empty_like(a)
+        _lib.check(_lib.load().fd_add(_p(a), _p(b), _p(out), a.numel(), _stream()), "fd_add")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return AddFn.apply(a, b)
+
+
+class MeanHWFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        _require_cuda(x, "mean_hw")
+        x = nhwc(x)
+        B, C, H, W = x.shape
+        y = torch.empty((B, C), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_mean_hw_fwd(_p(x), _p(y), B, H * W, C, scale, _stream()),
+                   "fd_mean_hw_fwd")
+        ctx.cfg = (B, C, H, W, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, H, W, scale = ctx.cfg
+        dy = dy.contiguous()
+        dx = empty_nhwc(B, C, H, W, dy.device)
+        _lib.check(_lib.load().fd_mean_hw_bwd(_p(dy), _p(dx), B, H * W, C, scale, _stream()),
+                   "fd_mean_hw_bwd")
+        return dx, None
+
+
+def mean_hw(x, scale=1.0):
+    return MeanHWFn.apply(x, float(scale))
+
+
+# --------------------------------------------------------------------------------------------
+LOSS_NAMES = ["loss/0", "loss/1", "loss/2", "loss/3", "loss/si_loss0", "loss/si_loss1",
+              "loss/si_loss2", "loss/si_loss3", "loss"]
+
+
+class PhotoLossFn(torch.autograd.Function):
+    """Fused generate_images_pred + compute_losses (trainer.py:425-596).
+
+    Differentiable inputs: the four disparities and the two poses.  Output: losses[9] in the
+    order of LOSS_NAMES; only losses[8] ("loss") carries gradient (that is the only entry the
+    reference back-propagates, trainer.py:244-245)."""
+
+    @staticmethod
+    def forward(ctx, d0, d1, d2, d3, T0, T1, static: Dict, opts: Dict, outs: Optional[Dict]):
+        lib = _lib.load()
+        _require_cuda(d0, "photoloss")
+        disps = [d.contiguous() for d in (d0, d1, d2, d3)]
+        T0, T1 = T0.contiguous(), T1.contiguous()
+        B, _, H, W = disps[0].shape
+        dev = d0.device
+        desc = _lib.PhotolossDesc()
+        desc.B, desc.H, desc.W = B, H, W
+        keep = []
+        for i, f in enumerate((0, -1, 1)):
+            for s in range(4):
+                t = static["color"].get((f, s))
+                if t is not None:
+                    t = t.contiguous()
+                    keep.append(t)
+                    desc.color[i][s] = t.data_ptr()
+        for s in range(4):
+            if disps[s].shape != (B, 1, H >> s, W >> s):
+                raise RuntimeError("photoloss: disp %d has shape %s" % (s, tuple(disps[s].shape)))
+            desc.disp[s] = disps[s].data_ptr()
+            n = static["noise"][s].contiguous()
+            keep.append(n)
+            desc.noise[s] = n.data_ptr()
+        K, invK, beam = static["K"].contiguous(), static["inv_K"].contiguous(), static["beam"].contiguous()
+        keep += [K, invK, beam]
+        desc.K, desc.inv_K, desc.beam = K.data_ptr(), invK.data_ptr(), beam.data_ptr()
+        desc.T[0], desc.T[1] = T0.data_ptr(), T1.data_ptr()
+        desc.min_depth, desc.max_depth = opts.get("min_depth", 0.1), opts.get("max_depth", 100.0)
+        desc.smoothness = opts.get("smoothness", 1e-3)
+        desc.si_thresh, desc.si_var = opts.get("si_thresh", 2.0), opts.get("si_var", 0.3)
+        desc.use_si = int(opts.get("use_si", True))
+        sel = torch.empty((4, B, H, W), device=dev, dtype=torch.uint8)
+        desc.sel = sel.data_ptr()
+        if outs is not None:
+            for s in range(4):
+                outs[("depth", 0, s)] = torch.empty((B, 1, H, W), device=dev)
+                desc.out_depth[s] = outs[("depth", 0, s)].data_ptr()
+                outs["to_optimise/%d" % s] = torch.empty((B, H, W), device=dev)
+                desc.out_to_optimise[s] = outs["to_optimise/%d" % s].data_ptr()
+                for j, f in enumerate((-1, 1)):
+                    outs[("color", f, s)] = torch.empty((B, 3, H, W), device=dev)
+                    desc.out_color[s][j] = outs[("color", f, s)].data_ptr()
+            outs["sel"] = sel
+        ws = torch.empty(lib.fd_photoloss_workspace_bytes(B, H, W) // 4, device=dev, dtype=torch.float32)
+        losses = torch.empty(9, device=dev, dtype=torch.float32)
+        _lib.check(lib.fd_photoloss_fwd(ctypes.byref(desc), _p(losses), _p(ws), _stream()),
+                   "fd_photoloss_fwd")
+        # the forward-only outputs must not be rewritten by the backward's descriptor
+        for s in range(4):
+            desc.out_depth[s] = None
+            desc.out_to_optimise[s] = None
+            desc.out_color[s][0] = None
+            desc.out_color[s][1] = None
+        ctx.desc, ctx.keep, ctx.ws, ctx.sel = desc, keep + disps + [T0, T1], ws, sel
+        ctx.shape = (B, H, W)
+        return losses
+
+    @staticmethod
+    def backward(ctx, glosses):
+        lib = _lib.load()
+        B, H, W = ctx.shape
+        dev = glosses.device
+        g = glosses[8:9].contiguous()
+        gd = [torch.empty((B, 1, H >> s, W >> s), device=dev, dtype=torch.float32) for s in range(4)]
+        gT0 = torch.empty((B, 4, 4), device=dev, dtype=torch.float32)
+        gT1 = torch.empty((B, 4, 4), device=dev, dtype=torch.float32)
+        arr = (c_void_p * 4)(*[t.data_ptr() for t in gd])
+        _lib.check(lib.fd_photoloss_bwd(ctypes.byref(ctx.desc), _p(g), ctypes.byref(arr), _p(gT0),
+                                        _p(gT1), _p(ctx.ws), _stream()), "fd_photoloss_bwd")
+        return gd[0], gd[1], gd[2], gd[3], gT0, gT1, None, None, None
+
+
+def photoloss(disps: Sequence[torch.Tensor], T_m1: torch.Tensor, T_p1: torch.Tensor, static: Dict,
+              opts: Optional[Dict] = None, outs: Optional[Dict] = None) -> torch.Tensor:
+    return PhotoLossFn.apply(disps[0], disps[1], disps[2], disps[3], T_m1, T_p1, static, opts or {},
+                             outs)
+
+
+# --------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """In-place Adam on flat fp32 buffers; `state` is a 4-word int32 device tensor (step counter)."""
+    _lib.check(_lib.load().fd_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
+                                        _p(state), grad_scale, _stream()), "fd_adam_step")

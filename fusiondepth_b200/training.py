@@ -1,0 +1,264 @@
+"""The per-step training hot path: six networks + fused photometric loss + Adam (+ DP all-reduce).
+
+Mirrors the call sequence of ``Trainer.process_batch`` / ``predict_poses`` /
+``generate_images_pred`` / ``compute_losses`` (reference trainer.py:268-596) with the reference's
+default flags (separate_resnet pose net on image pairs, beam encoders on, automasking, SSIM,
+si-loss on all scales), and of ``Trainer.run_epoch``'s accumulate-then-Adam loop
+(trainer.py:237-248).
+
+Two ways in:
+  * ``patch_trainer(trainer)`` -- keeps the reference's unchanged ``Trainer`` object and swaps
+    its ``generate_images_pred`` + ``compute_losses`` for the fused kernel pair;
+  * ``TrainStep`` -- the whole optimiser step (micro-batches, backward, gradient all-reduce, Adam
+    on flat buffers), optionally captured in one CUDA graph.  This is what bench.py times.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import networks, ops
+from .layers import transformation_from_parameters
+
+MODEL_NAMES = ("encoder", "beam_encoder", "beam_encoder_pose", "depth", "pose_encoder", "pose")
+
+
+def build_models(num_layers: int = 18, device="cuda", scales=(0, 1, 2, 3)) -> Dict[str, nn.Module]:
+    """The six networks of Trainer.__init__ (reference trainer.py:66-115), weights_init=scratch."""
+    m: Dict[str, nn.Module] = {}
+    m["encoder"] = networks.ResnetEncoder(num_layers, False)
+    m["beam_encoder"] = networks.ResnetEncoder(num_layers, False, beam_encoder=True)
+    m["beam_encoder_pose"] = networks.ResnetEncoder(num_layers, False, num_input_images=2,
+                                                    beam_encoder=True)
+    m["depth"] = networks.DepthDecoder(m["encoder"].num_ch_enc, list(scales))
+    m["pose_encoder"] = networks.ResnetEncoder(num_layers, False, num_input_images=2)
+    m["pose"] = networks.PoseDecoder(m["pose_encoder"].num_ch_enc, num_input_features=1,
+                                     num_frames_to_predict_for=2)
+    for k in m:
+        m[k].to(device)
+    return m
+
+
+def predict_poses(models, inputs, frame_ids=(0, -1, 1)):
+    """trainer.py:321-388, num_pose_frames == 2, separate_resnet, beam encoder on."""
+    outputs = {}
+    for f_i in frame_ids[1:]:
+        pair = (f_i, 0) if f_i < 0 else (0, f_i)          # temporal order (trainer.py:339-346)
+        img = torch.cat([inputs[("color_aug", i, 0)] for i in pair], 1)
+        two = torch.cat([inputs[("2channel", i, 0)] for i in pair], 1)
+        pf = [models["pose_encoder"](img)]
+        bf = [models["beam_encoder_pose"](two)]
+        axisangle, translation = models["pose"](pf, beam_inputs=bf)
+        outputs[("axisangle", 0, f_i)] = axisangle
+        outputs[("translation", 0, f_i)] = translation
+        outputs[("cam_T_cam", 0, f_i)] = transformation_from_parameters(
+            axisangle[:, 0], translation[:, 0], invert=(f_i < 0))
+    return outputs
+
+
+def loss_static(inputs, noise, frame_ids=(0, -1, 1)):
+    """Non-differentiable operands of the fused loss, gathered from the loader's dict."""
+    color = {}
+    for s in range(4):
+        color[(0, s)] = inputs[("color", 0, s)]
+    for f in frame_ids[1:]:
+        color[(f, 0)] = inputs[("color", f, 0)]
+    return {"color": color, "K": inputs[("K", 0)], "inv_K": inputs[("inv_K", 0)],
+            "beam": inputs["4beam"], "noise": noise}
+
+
+def fused_losses(inputs, outputs, noise, opts: Optional[Dict] = None, materialize: bool = False,
+                 frame_ids=(0, -1, 1)):
+    """generate_images_pred + compute_losses (trainer.py:425-596) in two kernel launches.
+    Returns the reference's ``losses`` dict; with ``materialize`` the per-scale
+    ("depth",0,s), ("color",f,s), identity_selection/s tensors are written into ``outputs``."""
+    outs = {} if materialize else None
+    disps = [outputs[("disp", s)] for s in range(4)]
+    lv = ops.photoloss(disps, outputs[("cam_T_cam", 0, frame_ids[1])],
+                       outputs[("cam_T_cam", 0, frame_ids[2])],
+                       loss_static(inputs, noise, frame_ids), opts, outs)
+    losses = {name: lv[i] for i, name in enumerate(ops.LOSS_NAMES)}
+    if materialize:
+        sel = outs.pop("sel")
+        for s in range(4):
+            outputs["identity_selection/%d" % s] = (sel[s] > 1).float()
+        outputs.update(outs)
+        for f in frame_ids[1:]:
+            for s in range(4):
+                outputs[("color_identity", f, s)] = inputs[("color", f, 0)]
+    return losses
+
+
+def draw_noise(B, H, W, device):
+    """The tie-break noise exactly as the reference draws it: CPU generator, one [B,2,H,W] randn
+    per scale, then copied to the device (trainer.py:551-552)."""
+    return {s: torch.randn(B, 2, H, W).to(device) for s in range(4)}
+
+
+def process_batch(models, inputs, noise=None, opts: Optional[Dict] = None, materialize=False,
+                  frame_ids=(0, -1, 1)):
+    """Trainer.process_batch (trainer.py:268-319), default flags."""
+    feats = models["encoder"](inputs[("color_aug", 0, 0)])
+    beam = models["beam_encoder"](inputs["2channel"])
+    outputs = dict(models["depth"](feats, beam_features=beam))
+    outputs.update(predict_poses(models, inputs, frame_ids))
+    if noise is None:
+        B, _, H, W = inputs[("color", 0, 0)].shape
+        noise = draw_noise(B, H, W, inputs[("color", 0, 0)].device)
+    losses = fused_losses(inputs, outputs, noise, opts, materialize, frame_ids)
+    return outputs, losses
+
+
+def patch_trainer(trainer, materialize: bool = True):
+    """Swap the reference Trainer's warp + loss methods for the fused kernels, in place."""
+    opt = trainer.opt
+    if (opt.v1_multiscale or opt.disable_automasking or opt.avg_reprojection or opt.no_ssim
+            or opt.predictive_mask or opt.use_stereo or opt.pose_model_type == "posecnn"
+            or list(opt.scales) != [0, 1, 2, 3] or list(opt.frame_ids) != [0, -1, 1]):
+        raise NotImplementedError("patch_trainer covers the reference's default loss configuration")
+    opts = {"min_depth": opt.min_depth, "max_depth": opt.max_depth,
+            "smoothness": opt.disparity_smoothness, "si_thresh": opt.gdc_loss_threshold,
+            "si_var": opt.si_var,
+            "use_si": opt.trainer_siloss == "true" and opt.trainer_siloss_all_scale}
+
+    def generate_images_pred(inputs, outputs, frame_ids):
+        return None                                   # done inside the fused loss launch
+
+    def compute_losses(inputs, outputs):
+        B, _, H, W = inputs[("color", 0, 0)].shape
+        return fused_losses(inputs, outputs, draw_noise(B, H, W, inputs[("color", 0, 0)].device),
+                            opts, materialize)
+
+    trainer.generate_images_pred = generate_images_pred
+    trainer.compute_losses = compute_losses
+    return trainer
+
+
+# ------------------------------------------------------------------------------------------------
+class FlatParams:
+    """All trainable parameters (and their gradients) as views of two flat fp32 buffers, so that
+    the data-parallel gradient exchange is one all-reduce and Adam is one kernel.  Conv weights
+    keep their channels-last storage order inside the buffer."""
+
+    def __init__(self, models: Dict[str, nn.Module]):
+        params: List[nn.Parameter] = []
+        for name in models:
+            params += [p for p in models[name].parameters() if p.requires_grad]
+        self.params = params
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.data = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            k = p.numel()
+            dv, gv = self._view(self.data[off:off + k], p), self._view(self.grad[off:off + k], p)
+            dv.copy_(p.data)
+            p.data = dv
+            p.grad = gv
+            off += k
+        self.numel = n
+
+    @staticmethod
+    def _view(flat, p):
+        if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+            o, i, kh, kw = p.shape
+            return flat.view(o, kh, kw, i).permute(0, 3, 1, 2)
+        return flat.view(p.shape)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+class TrainStep:
+    """One optimiser step of trainer.py:237-248: ``accumulate`` micro-batches, each
+    process_batch -> (loss/accumulate).backward(), then Adam.  With world_size > 1 the flat
+    gradient buffer is averaged across ranks with one NCCL all-reduce before Adam."""
+
+    def __init__(self, models, lr: float = 1e-4, accumulate: int = 1, opts: Optional[Dict] = None,
+                 process_group=None):
+        self.models = models
+        self.accumulate = accumulate
+        self.lr = float(lr)
+        self.opts = opts
+        self.flat = FlatParams(models)
+        dev = self.flat.data.device
+        self.exp_avg = torch.zeros_like(self.flat.data)
+        self.exp_avg_sq = torch.zeros_like(self.flat.data)
+        self.adam_state = torch.zeros(4, device=dev, dtype=torch.int32)
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.graph = None
+        self.static_inputs = None
+        self.static_noise = None
+        self.loss_out = None
+        for m in models.values():
+            m.train()
+
+    # -- eager -------------------------------------------------------------------------------
+    def _run(self, batches: Sequence[Dict], noises: Sequence[Dict]):
+        self.flat.zero_grad()
+        total = None
+        for inputs, noise in zip(batches, noises):
+            _, losses = process_batch(self.models, inputs, noise, self.opts)
+            loss = losses["loss"] / self.accumulate
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat.grad, group=self.pg)
+        ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.adam_state,
+                      self.lr, grad_scale=1.0 / self.world)
+        return total
+
+    def step(self, batches: Sequence[Dict], noises: Sequence[Dict]):
+        assert len(batches) == self.accumulate
+        return self._run(batches, noises)
+
+    # -- CUDA graph ----------------------------------------------------------------------------
+    def capture(self, batches: Sequence[Dict], noises: Sequence[Dict], warmup: int = 2):
+        """Captures the whole step over static copies of the inputs; ``replay`` then costs one
+        graph launch.  Warm-up steps run on a side stream first (allocator + NCCL warm)."""
+        self.static_inputs = [{k: v.clone() for k, v in b.items()} for b in batches]
+        self.static_noise = [{k: v.clone() for k, v in n.items()} for n in noises]
+        keep = (self.flat.data.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
+                self.adam_state.clone(), self._bn_state())
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._run(self.static_inputs, self.static_noise)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss_out = self._run(self.static_inputs, self.static_noise)
+        # undo the warm-up / capture side effects on the training state
+        self.flat.data.copy_(keep[0]); self.exp_avg.copy_(keep[1]); self.exp_avg_sq.copy_(keep[2])
+        self.adam_state.copy_(keep[3]); self._bn_state(keep[4])
+        torch.cuda.synchronize()
+
+    def load_inputs(self, batches: Sequence[Dict], noises: Sequence[Dict]):
+        for dst, src in zip(self.static_inputs, batches):
+            for k in dst:
+                dst[k].copy_(src[k], non_blocking=True)
+        for dst, src in zip(self.static_noise, noises):
+            for k in dst:
+                dst[k].copy_(src[k], non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss_out
+
+    def _bn_state(self, restore=None):
+        bufs = []
+        for m in self.models.values():
+            bufs += [b for _, b in m.named_buffers()]
+        if restore is None:
+            return [b.clone() for b in bufs]
+        for b, r in zip(bufs, restore):
+            b.copy_(r)

@@ -1,0 +1,167 @@
+/*
+ * fusiondepth_b200 -- C ABI of the B200 (sm_100a) kernels behind the FusionDepth per-step
+ * training hot path.
+ *
+ * The reference (AutoAILab/FusionDepth) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it exposes for this path is the Python module surface `layers.*` / `networks.*`
+ * (see INTEGRATION.md).  Each entry point below replaces the ATen op sequence behind one
+ * reference function and cites it (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless the name ends in
+ *     `_host`; the library never allocates, frees or retains device memory;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, no internal syncs,
+ *     capturable in CUDA graphs;
+ *   - return 0 on success; non-zero => fd_last_error() describes the failure;
+ *   - activations are fp32 NHWC ("channels last"), conv weights fp32 [Cout,KH,KW,Cin];
+ *     images of the loss chain are fp32 NCHW as the reference's loader delivers them.
+ */
+#ifndef FUSIONDEPTH_B200_H
+#define FUSIONDEPTH_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* fd_last_error(void);
+int fd_version(void);
+/* number of kernel launches issued through this library since load (for bench gpu_launches) */
+long fd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse LiDAR  (bit-exact)
+ * ---------------------------------------------------------------------------------------- */
+
+/* kitti_utils.generate_depth_map (kitti_utils.py:40-102), batched over frames.
+ *   points  [n_points_total,4] float32 velodyne points of all frames, concatenated
+ *   offsets [n_frames+1] int32 prefix offsets into points
+ *   P       [n_frames,12] float64: P_rect_0x @ R_rect_00 @ Tr_velo_to_cam (kitti_utils.py:53-56)
+ *   shape_h/shape_w: the `shape` argument (0,0 = None); depth_out [n_frames,out_h,out_w] float64
+ *   workspace: fd_lidar_workspace_bytes() bytes */
+size_t fd_lidar_workspace_bytes(int n_frames, int W_im, int H_im);
+int fd_lidar_depth_map(const float* points, const int* offsets, int n_frames, int n_points_total,
+                       const double* P, int W_im, int H_im, int vel_depth, int shape_h,
+                       int shape_w, double* depth_out, int out_h, int out_w, void* workspace,
+                       void* stream);
+
+/* F.max_pool2d(.,2,ceil_mode=True) -> float32 -> /100.0  (kitti_dataset.py:105-107,
+ * mono_dataset.py:194-198).  depth [n,H,W] float64 -> out [n,ceil(H/2),ceil(W/2)] float32 */
+int fd_lidar_pool_scale(const double* depth, int n_frames, int H, int W, float* out, void* stream);
+
+/* get_4beam_2channel (gen2channel.py:60-117).  fourbeam [n,H,W] -> out [n,2,H,W]
+ * (expanded depth, confidence); source window rows [r0,r1) cols [c0,c1)
+ * (reference: 76,190,2,638 at 192x640). */
+int fd_two_channel(const float* fourbeam, int n_frames, int H, int W, int r0, int r1, int c0, int c1,
+                   float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused photometric loss chain
+ *   trainer.generate_images_pred + compute_losses (trainer.py:425-596) and the layers.* they
+ *   call (layers.py:11-20,133-162,204-226,235-281), default flags.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fd_photoloss_desc {
+  int B, H, W;
+  /* color[i][s]: frame_ids[i] (0, -1, +1) at scale s, [B,3,H>>s,W>>s] NCHW.  Only scale 0 of the
+   * source frames is read (source_scale = 0, trainer.py:436,503). */
+  const float* color[3][4];
+  const float* disp[4];       /* [B,1,H>>s,W>>s] network output ("disp", s) */
+  const float* K;             /* [B,4,4] ("K",0) */
+  const float* inv_K;         /* [B,4,4] ("inv_K",0) */
+  const float* T[2];          /* [B,4,4] cam_T_cam for frames -1, +1 */
+  const float* noise[4];      /* [B,2,H,W] the randn of trainer.py:551 per scale */
+  const float* beam;          /* [B,1,H,W] inputs["4beam"] */
+  float min_depth, max_depth; /* options.py:64-71 (0.1, 100) */
+  float smoothness;           /* disparity_smoothness 1e-3 */
+  float si_thresh, si_var;    /* gdc_loss_threshold 2.0, si_var 0.3 */
+  int use_si;                 /* trainer_siloss on all scales */
+  unsigned char* sel;         /* [4,B,H,W] out: argmin channel (0,1 identity; 2,3 warped) */
+  float* out_depth[4];        /* optional [B,1,H,W] ("depth",0,s) */
+  float* out_color[4][2];     /* optional [B,3,H,W] ("color",f,s) */
+  float* out_to_optimise[4];  /* optional [B,H,W] */
+} fd_photoloss_desc;
+
+size_t fd_photoloss_workspace_bytes(int B, int H, int W);
+/* losses[9] = loss/0..3, loss/si_loss0..3, loss.  The workspace carries the state the backward
+ * needs and must be the same buffer in both calls. */
+int fd_photoloss_fwd(const fd_photoloss_desc* desc_host, float* losses, void* workspace, void* stream);
+/* grad_loss: device scalar d/d losses["loss"].  grad_disp[s] [B,1,H>>s,W>>s]; grad_T [B,4,4]. */
+int fd_photoloss_bwd(const fd_photoloss_desc* desc_host, const float* grad_loss,
+                     float* const grad_disp[4], float* grad_T0, float* grad_T1, void* workspace,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Network operators (NHWC fp32).  Replace the ATen/cuDNN ops under networks/resnet_encoder.py,
+ * networks/depth_decoder.py, networks/pose_decoder.py, networks/pose_cnn.py, layers.ConvBlock /
+ * Conv3x3 (layers.py:100-130) and torchvision's BasicBlock/Bottleneck.
+ * ---------------------------------------------------------------------------------------- */
+enum { FD_ACT_NONE = 0, FD_ACT_RELU = 1, FD_ACT_ELU = 2, FD_ACT_SIGMOID = 3, FD_ACT_TANH = 4 };
+
+/* (x-0.45)/0.225 + NCHW->NHWC  (resnet_encoder.py:94) */
+int fd_prep_input(const float* x_nchw, float* y_nhwc, int B, int C, int H, int W, float mean,
+                  float std, void* stream);
+
+/* y = act(conv(x, w) + bias); zero padding `pad`.  x [B,H,W,Cin], w [Cout,KH,KW,Cin],
+ * y [B,Ho,Wo,Cout], Ho = (H+2*pad-KH)/stride+1. */
+int fd_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                  int Cin, int Cout, int KH, int KW, int stride, int pad, int act, void* stream);
+/* dx = conv_transpose(dy, w).  wt = fd_weight_transpose(w): [Cin,KH,KW,Cout]. */
+int fd_conv2d_dgrad(const float* dy, const float* wt, float* dx, int B, int H, int W, int Cin,
+                    int Cout, int KH, int KW, int stride, int pad, void* stream);
+/* dw [Cout,KH,KW,Cin] += sum over pixels; dw must be zero-initialised (or hold an accumulator) */
+int fd_conv2d_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin,
+                    int Cout, int KH, int KW, int stride, int pad, void* stream);
+int fd_weight_transpose(const float* w, float* wt, int Cout, int taps, int Cin, void* stream);
+/* dpre = dy * act'(.) computed from the activation output y; dbias[c] += sum_m dpre[m,c] */
+int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long M, int C, int act,
+               void* stream);
+
+/* BatchNorm2d (+ optional residual add, + optional ReLU) over M = B*H*W rows of C channels.
+ * training: batch statistics, running stats updated (momentum, unbiased var).
+ * ws: 2*C doubles of scratch.  save_mean/save_rstd [C] are outputs used by the backward. */
+int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
+              float* running_mean, float* running_var, int training, float momentum, float eps,
+              int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
+              void* stream);
+int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
+              const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
+              float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
+              void* stream);
+
+/* nn.MaxPool2d(3, 2, 1)  (ResNet stem) */
+int fd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C,
+                        void* stream);
+int fd_maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, float* dx, int B, int H, int W,
+                        int C, void* stream);
+
+/* Decoder glue: out = reflect_pad_p( concat_c( seg_0, seg_1, ... ) ), where each segment is
+ * (a [+ b]) optionally nearest-upsampled x2  (layers.upsample, torch.cat, ReflectionPad2d in
+ * depth_decoder.py:73-85 / layers.py:121-130).  out [B,H+2p,W+2p,sum C]. */
+typedef struct fd_segment {
+  const float* a;
+  const float* b; /* nullable: added to a */
+  int C;
+  int up; /* 1: source is [B,H/2,W/2,C] */
+} fd_segment;
+int fd_assemble_fwd(const fd_segment* segs_host, int nseg, float* out, int B, int H, int W, int pad,
+                    void* stream);
+/* dseg[i] [B,Hs,Ws,C_i] = adjoint (gather form, deterministic) */
+int fd_assemble_bwd(const float* dout, float* const* dsegs_host, const int* C_host,
+                    const int* up_host, int nseg, int B, int H, int W, int pad, void* stream);
+
+int fd_add(const float* a, const float* b, float* out, long n, void* stream);
+/* y[b,c] = scale * mean_hw x[b,:,c]  (pose_decoder.py:44-46) */
+int fd_mean_hw_fwd(const float* x, float* y, int B, int HW, int C, float scale, void* stream);
+int fd_mean_hw_bwd(const float* dy, float* dx, int B, int HW, int C, float scale, void* stream);
+
+/* torch.optim.Adam update on flat buffers (trainer.py:129): g is multiplied by grad_scale first.
+ * state: 4 x int32 device words, state[0] = number of steps taken so far (incremented here, on
+ * the device, so that a captured CUDA graph advances the bias correction on every replay). */
+int fd_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                 float beta2, float eps, int* state, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

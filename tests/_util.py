@@ -1,0 +1,61 @@
+"""Shared helpers for the test-suite (deterministic weights, tolerances, paths)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _seed_of(key: str, seed: int) -> int:
+    return int.from_bytes(hashlib.sha256(("%d/%s" % (seed, key)).encode()).digest()[:4], "little")
+
+
+def synth_weights(template: "OrderedDict[str, torch.Tensor]", seed: int = 0):
+    """Deterministic weights for a state_dict *template* (only key -> shape/dtype is used),
+    independent of module construction order: every tensor is drawn from its own generator
+    seeded by hash(seed, key).  Conv/linear weights ~ N(0, 2/fan_out); BN weight ~ U(.5,1.5);
+    biases, running_mean ~ small normal; running_var ~ U(.5,1.5)."""
+    out = OrderedDict()
+    for k, t in template.items():
+        g = torch.Generator().manual_seed(_seed_of(k, seed))
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith("running_var"):
+            out[k] = 0.5 + torch.rand(t.shape, generator=g)
+        elif k.endswith("running_mean"):
+            out[k] = 0.1 * torch.randn(t.shape, generator=g)
+        elif t.dim() >= 2:
+            fan_out = t.shape[0] * int(np.prod(t.shape[2:])) if t.dim() == 4 else t.shape[0]
+            out[k] = torch.randn(t.shape, generator=g) * float(np.sqrt(2.0 / fan_out))
+        elif ".bn" in k or "downsample.1" in k:
+            out[k] = (0.5 + torch.rand(t.shape, generator=g)) if k.endswith("weight") \
+                else 0.1 * torch.randn(t.shape, generator=g)
+        else:
+            out[k] = 0.05 * torch.randn(t.shape, generator=g)
+    return out
+
+
+def clone_sd(sd, requires_grad=False):
+    out = OrderedDict()
+    for k, v in sd.items():
+        t = v.detach().clone()
+        if requires_grad and t.is_floating_point() and not (
+                k.endswith("running_mean") or k.endswith("running_var")):
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+def rel_err(a, b) -> float:
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

@@ -1,0 +1,219 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only:  python tests/make_golden.py
+The fixtures pin the oracle (oracle/) -- the reference ships no golden vectors of its own
+ and cannot travel to the GPU box.  Inputs are regenerated from seeds
+by fusiondepth_b200.synth / tests._util.synth_weights; only small inputs that cannot be
+regenerated bit-exactly are stored.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import _refharness as RH            # noqa: E402
+from tests._util import GOLDEN, synth_weights   # noqa: E402
+from fusiondepth_b200 import synth              # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def lidar_cases():
+    return {
+        "ring4": synth.make_scan(3),
+        "piled": synth.make_scan(5, piled=600),
+        "dense": synth.make_dense_scan(7, n=30000),
+        "edge": synth.make_dense_scan(9, n=20000, edge_heavy=True),
+    }
+
+
+def gen_lidar(ns):
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_calib_files(d)
+        for name, pts in lidar_cases().items():
+            fn = os.path.join(d, name + ".bin")
+            p = pts.copy()
+            p.tofile(fn)
+            out[name + "/points"] = pts
+            dm = ns.kitti_utils.generate_depth_map(d, fn, 2, shape=[384, 1280])
+            out[name + "/depth384"] = dm
+            raw = ns.kitti_utils.generate_depth_map(d, fn, 2)
+            out[name + "/depth_raw"] = raw
+            if name in ("ring4", "edge"):
+                out[name + "/depth_vel375"] = ns.kitti_utils.generate_depth_map(
+                    d, fn, 3, vel_depth=True, shape=[375, 1242])
+            # kitti_dataset.py:105-107 + mono_dataset.py:194-198
+            fb = F.max_pool2d(torch.tensor(dm).unsqueeze(0), 2, ceil_mode=True).squeeze().numpy()
+            fb = torch.from_numpy(np.expand_dims(fb, 0).astype(np.float32)) / 100.0
+            out[name + "/4beam"] = fb[0].numpy()
+            e, c = ns.get_4beam_2channel(fb[0])
+            out[name + "/2channel"] = torch.stack([e, c]).numpy()
+            print("lidar", name, pts.shape, int((dm > 0).sum()), int((fb > 0).sum()))
+    # random-density inputs for get_4beam_2channel
+    for dens in (0.02, 0.15, 0.5):
+        g = torch.Generator().manual_seed(int(dens * 1000))
+        fb = (torch.rand(192, 640, generator=g) < dens).float() * (0.02 + torch.rand(192, 640, generator=g))
+        e, c = ns.get_4beam_2channel(fb)
+        out["rand%03d/4beam" % int(dens * 100)] = fb.numpy()
+        out["rand%03d/2channel" % int(dens * 100)] = torch.stack([e, c]).numpy()
+        print("2channel density", dens)
+    np.savez_compressed(os.path.join(GOLDEN, "lidar.npz"), **out)
+
+
+def _load_weights(models, seed):
+    for i, (name, m) in enumerate(sorted(models.items())):
+        m.load_state_dict(synth_weights(m.state_dict(), seed * 100 + i))
+
+
+def gen_step(ns, B=2, H=64, W=96):
+    """Full Trainer.process_batch + backward (config 2 semantics at a small size)."""
+    models = RH.make_models(ns, 18)
+    _load_weights(models, 0)
+    for m in models.values():
+        m.train()
+    tr = RH.make_trainer(ns, models, B, H, W)
+    inputs = synth.make_batch(B, H, W, seed=1)
+    noise = inputs.pop("noise")
+    with RH.FixedNoise([noise[s] for s in range(4)]):
+        outputs, losses = tr.process_batch(dict(inputs))
+    losses["loss"].backward()
+    out = {}
+    for s in range(4):
+        out["disp%d" % s] = outputs[("disp", s)].detach().numpy()
+        out["identity_selection%d" % s] = outputs["identity_selection/%d" % s].numpy()
+        out["depth%d" % s] = outputs[("depth", 0, s)].detach().numpy()
+    for f in (-1, 1):
+        out["cam_T_cam%d" % f] = outputs[("cam_T_cam", 0, f)].detach().numpy()
+        out["axisangle%d" % f] = outputs[("axisangle", 0, f)].detach().numpy()
+        out["translation%d" % f] = outputs[("translation", 0, f)].detach().numpy()
+        out["color%d_0" % f] = outputs[("color", f, 0)].detach().numpy()
+    for k, v in losses.items():
+        out["loss:" + k] = v.detach().numpy()
+    for name, m in sorted(models.items()):
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                out["gnorm:%s/%s" % (name, k)] = p.grad.double().norm().numpy()
+        for k, b in m.named_buffers():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                out["buf:%s/%s" % (name, k)] = b.double().norm().numpy()
+        out["grad:%s/last" % name] = list(m.parameters())[-1].grad.numpy() \
+            if list(m.parameters())[-1].grad is not None else np.zeros(1)
+    out["grad:encoder/conv1"] = models["encoder"].encoder.conv1.weight.grad.numpy()
+    out["grad:depth/decoder.0"] = models["depth"].decoder[0].conv.conv.weight.grad.numpy()[:8]
+    np.savez_compressed(os.path.join(GOLDEN, "step_r18.npz"), **out)
+    print("step_r18", {k: float(v) for k, v in losses.items()})
+
+
+def gen_forward_variants(ns, H=64, W=96):
+    """Config 1 (enc+beam enc+decoder forward, eval mode) for R18 and R50, plus the stage-2
+    refine2d decoder (road,catxy,deep) and PoseCNN forward."""
+    N = ns.networks
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    rgb = torch.rand(1, 3, H, W, generator=g)
+    two = torch.rand(1, 2, H, W, generator=g) * (torch.rand(1, 1, H, W, generator=g) < 0.1)
+    out["rgb"], out["two"] = rgb.numpy(), two.numpy()
+    for nl in (18, 50):
+        enc = N.ResnetEncoder(nl, False)
+        benc = N.ResnetEncoder(nl, False, beam_encoder=True)
+        dec = N.DepthDecoder(enc.num_ch_enc, [0, 1, 2, 3])
+        for i, m in enumerate((enc, benc, dec)):
+            m.load_state_dict(synth_weights(m.state_dict(), 1000 + nl * 10 + i))
+            m.eval()
+        with torch.no_grad():
+            feats, bf = enc(rgb), benc(two)
+            feats = [f.clone() for f in feats]
+            d = dec(feats, beam_features=bf)
+        for s in range(4):
+            out["r%d/disp%d" % (nl, s)] = d[("disp", s)].numpy()
+        out["r%d/feat4" % nl] = feats[4].numpy()
+        if nl == 18:
+            ref2d = N.DepthDecoder(enc.num_ch_enc, [0, 1, 2, 3], road=True, catxy=True, deep=True)
+            ref2d.load_state_dict(synth_weights(ref2d.state_dict(), 2000))
+            ref2d.eval()
+            dm = {("disp", s): torch.rand(1, 6, H >> s, W >> s, generator=g) for s in range(4)}
+            with torch.no_grad():
+                r = ref2d(feats, beam_features=bf, depth_maps=dm, tanh=False)
+            for s in range(4):
+                out["refine/dm%d" % s] = dm[("disp", s)].numpy()
+                out["refine/disp%d" % s] = r[("disp", s)].numpy()
+    pc = N.PoseCNN(2)
+    pc.load_state_dict(synth_weights(pc.state_dict(), 3000))
+    with torch.no_grad():
+        aa, tt = pc(torch.cat([rgb, rgb.flip(3)], 1))
+    out["posecnn/aa"], out["posecnn/t"] = aa.numpy(), tt.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "forward_variants.npz"), **out)
+    print("forward variants done")
+
+
+def gen_loss_chain(ns, B=2, H=96, W=160):
+    """generate_images_pred + compute_losses alone on coherent frames, with grads wrt the
+    four disparities and the two poses."""
+    models = {}
+    tr = RH.make_trainer(ns, models, B, H, W)
+    inputs = synth.make_batch(B, H, W, seed=5, mode="coherent")
+    noise = inputs.pop("noise")
+    g = torch.Generator().manual_seed(77)
+    outputs = {}
+    leaves = {}
+    for s in range(4):
+        low = torch.rand(B, 1, (H >> s) // 4 + 2, (W >> s) // 4 + 2, generator=g)
+        d = torch.sigmoid(3 * (F.interpolate(low, (H >> s, W >> s), mode="bilinear",
+                                             align_corners=False) - 0.5) - 1.0)
+        d = d + 0.01 * torch.rand(B, 1, H >> s, W >> s, generator=g)
+        leaves["disp%d" % s] = d.clone().requires_grad_(True)
+        outputs[("disp", s)] = leaves["disp%d" % s]
+    for f in (-1, 1):
+        aa = (0.01 * torch.randn(B, 1, 3, generator=g)).requires_grad_(True)
+        tt = (0.05 * torch.randn(B, 1, 3, generator=g)).requires_grad_(True)
+        leaves["aa%d" % f], leaves["tt%d" % f] = aa, tt
+        T = ns.layers.transformation_from_parameters(aa, tt, invert=(f < 0))
+        T.retain_grad()
+        leaves["T%d" % f] = T
+        outputs[("cam_T_cam", 0, f)] = T
+    # beam map consistent with depth*26 so the si-loss mask is populated
+    with torch.no_grad():
+        up = F.interpolate(leaves["disp0"], [H, W], mode="bilinear", align_corners=False)
+        dep = 26.0 / (0.01 + 9.99 * up)
+        mask = (torch.rand(B, 1, H, W, generator=g) < 0.05).float()
+        inputs["4beam"] = mask * (dep + (torch.rand(B, 1, H, W, generator=g) - 0.5) * 3.0) / 100.0
+    tr.generate_images_pred(inputs, outputs, [0, -1, 1])
+    with RH.FixedNoise([noise[s] for s in range(4)]):
+        losses = tr.compute_losses(inputs, outputs)
+    losses["loss"].backward()
+    out = {"4beam": inputs["4beam"].numpy()}
+    for k, v in leaves.items():
+        out["in:" + k] = v.detach().numpy()
+        out["grad:" + k] = v.grad.numpy()
+    for k, v in losses.items():
+        out["loss:" + k] = v.detach().numpy()
+    for s in range(4):
+        out["identity_selection%d" % s] = outputs["identity_selection/%d" % s].numpy()
+        out["depth%d" % s] = outputs[("depth", 0, s)].detach().numpy()
+        if s in (0, 3):
+            for f in (-1, 1):
+                out["color%d_%d" % (f, s)] = outputs[("color", f, s)].detach().numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "loss_chain.npz"), **out)
+    print("loss_chain", {k: float(v) for k, v in losses.items()})
+
+
+if __name__ == "__main__":
+    assert RH.available(), "needs /root/reference (build container only)"
+    os.makedirs(GOLDEN, exist_ok=True)
+    ns = RH.load()
+    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss"]
+    if "lidar" in which:
+        gen_lidar(ns)
+    if "step" in which:
+        gen_step(ns)
+    if "fwd" in which:
+        gen_forward_variants(ns)
+    if "loss" in which:
+        gen_loss_chain(ns)
