@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the FusionDepth per-step training hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on host cores
+
+Metric (BASELINE.json): training images/sec at 640x192, batch 12 (the reference runs
+`--batch_size 12` as two micro-batches of 6 with loss/2 and one Adam step, trainer.py:30-41,
+237-248).  One "step" = one optimiser step = 12 images per GPU: 6 ResNet-18 trunks +
+DepthDecoder + 2 PoseDecoders forward/backward per micro-batch, the fused photometric loss
+chain, gradient all-reduce (N>1) and Adam.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W, MICRO_B, ACCUM = 192, 640, 6, 2
+NUM_LAYERS = 18
+METRIC = "training images/sec (640x192 b12)"
+CONV_GFLOP_PER_IMAGE = 182.4            # fwd+bwd, BASELINE.md section 4
+LOSS_BYTES_PER_IMAGE = 431.8 * H * W    # fwd+bwd algorithmic bytes, SURVEY.md section 8(d)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tf": p["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm": 6650.0, "tf": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_step_inputs(seed: int, device=None):
+    """ACCUM micro-batches of MICRO_B images (CPU tensors); 4-beam scans go through the CUDA LiDAR
+    kernels when a device is given, else through the stand-in."""
+    from fusiondepth_b200 import synth
+    lidar_fn = None
+    if device is not None:
+        from fusiondepth_b200 import lidar
+        P = synth.velo_to_image_matrix(synth.parse_roundtrip(), 2)
+
+        def lidar_fn(points):
+            fb, two = lidar.lidar_inputs([points], [P], device=device)
+            return {"4beam": fb[0].cpu(), "2channel": two[0].cpu()}
+    batches, noises = [], []
+    for i in range(ACCUM):
+        b = synth.make_batch(MICRO_B, H, W, seed=seed * 10 + i, lidar_fn=lidar_fn, mode="coherent")
+        noises.append(b.pop("noise"))
+        batches.append(b)
+    return batches, noises
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's algorithm on host cores (the oracle port: /root/reference is pure Python
+    and does not exist on the GPU box).  Each step = one micro-batch of 6 images fwd+bwd + Adam."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import step_oracle as SO
+    from fusiondepth_b200 import training
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    torch.manual_seed(0)
+    models = training.build_models(NUM_LAYERS, "cpu")
+    sds = {}
+    for name, m in models.items():
+        sds[name] = {k: (v.detach().clone().contiguous().requires_grad_(True)
+                         if v.is_floating_point() and "running" not in k else v.detach().clone())
+                     for k, v in m.state_dict().items()}
+    params = [t for sd in sds.values() for t in sd.values() if t.requires_grad]
+    m1, m2 = [torch.zeros_like(p) for p in params], [torch.zeros_like(p) for p in params]
+    batches, noises = synthetic_step_inputs(1)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for p in params:
+            p.grad = None
+        _, losses = SO.process_batch(sds, batches[it % ACCUM], noises[it % ACCUM], NUM_LAYERS, True)
+        (losses["loss"] / ACCUM).backward()
+        with torch.no_grad():
+            live = [(p, a, b) for p, a, b in zip(params, m1, m2) if p.grad is not None]
+            SO.adam_step([x[0] for x in live], [x[0].grad for x in live], [x[1] for x in live],
+                         [x[2] for x in live], it + 1, 1e-4 * 12 / 8)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = MICRO_B / (ms / 1e3)
+    sample = "1 micro-batch of %d images (fwd+bwd+Adam) per step, oracle port, fp32" % MICRO_B
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": 0,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "trainer.py step, ResNet-18, 640x192, batch 12 (2 x 6), host CPU"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_leg():
+    """Bounded CPU sample on rank 0: one optimiser step (2 micro-batches of 6) after one warm-up
+    micro-batch, through the oracle port."""
+    from oracle import step_oracle as SO
+    from fusiondepth_b200 import training
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    models = training.build_models(NUM_LAYERS, "cpu")
+    sds = {name: {k: (v.detach().clone().contiguous().requires_grad_(True)
+                      if v.is_floating_point() and "running" not in k else v.detach().clone())
+                  for k, v in m.state_dict().items()} for name, m in models.items()}
+    batches, noises = synthetic_step_inputs(2)
+    _, l = SO.process_batch(sds, batches[0], noises[0], NUM_LAYERS, True)
+    (l["loss"] / ACCUM).backward()
+    t0 = time.perf_counter()
+    for b, n in zip(batches, noises):
+        _, l = SO.process_batch(sds, b, n, NUM_LAYERS, True)
+        (l["loss"] / ACCUM).backward()
+    dt = time.perf_counter() - t0
+    return {"value": MICRO_B * ACCUM / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "1 optimiser step (2 micro-batches of 6, fwd+bwd) after 1 warm-up micro-batch"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from fusiondepth_b200 import _lib, ops, synth, training
+    _lib.load()                                   # no CUDA extension => fail loudly
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)                          # same initial weights on every rank
+    models = training.build_models(NUM_LAYERS, dev)
+    step = training.TrainStep(models, lr=1e-4 * (MICRO_B * ACCUM) / 8, accumulate=ACCUM)
+    cpu_batches, cpu_noises = synthetic_step_inputs(100 + rank, dev)
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in cpu_batches]
+    pinned_noise = [{k: v.pin_memory() for k, v in n.items()} for n in cpu_noises]
+    h2d = sum(v.numel() * v.element_size() for b in pinned for v in b.values()) + \
+        sum(v.numel() * v.element_size() for n in pinned_noise for v in n.values())
+    batches = [synth.to_device(b, dev) for b in cpu_batches]
+    noises = [{s: t.to(dev) for s, t in n.items()} for n in cpu_noises]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    if args.profile_step:
+        step.step(batches, noises)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step.step(batches, noises)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
+
+    n0 = _lib.launch_count()
+    if args.no_graph:
+        run = lambda: step.step(batches, noises)
+        run()
+        launches_per_step = _lib.launch_count() - n0
+    else:
+        step.capture(batches, noises, warmup=1)
+        launches_per_step = (_lib.launch_count() - n0) // 2      # 1 warm-up + 1 capture pass
+        run = step.replay
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t) / k, out
+
+    first_loss = float(run())
+    for _ in range(max(args.warmup, 3) - 1):
+        run()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, loss = timed(run, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end: pinned host inputs -> H2D -> step -> D2H loss, every step
+    host_loss = torch.empty(1).pin_memory()
+
+    def e2e_step():
+        if args.no_graph:
+            b = [synth.to_device(x, dev) for x in pinned]
+            n = [{s: t.to(dev, non_blocking=True) for s, t in x.items()} for x in pinned_noise]
+            out = step.step(b, n)
+        else:
+            step.load_inputs(pinned, pinned_noise)
+            out = step.replay()
+        host_loss.copy_(out.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host_loss
+
+    e2e_step()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+
+    result = None
+    if rank == 0:
+        imgs = MICRO_B * ACCUM * world
+        pk = peaks()
+        # per-kernel-family device times from one instrumented eager step
+        ops.PROFILE = {}
+        step.step(batches, noises)
+        torch.cuda.synchronize()
+        fam = {}
+        for name, evs in ops.PROFILE.items():
+            fam[name] = (sum(s.elapsed_time(e) for s, e, _ in evs), sum(w for _, _, w in evs), len(evs))
+        ops.PROFILE = None
+        conv_ms, conv_flop, conv_n = fam.get("conv", (0.0, 0.0, 0))
+        pl_ms = fam["photoloss_fwd"][0] + fam["photoloss_bwd"][0]
+        pl_bytes = fam["photoloss_fwd"][1] + fam["photoloss_bwd"][1]
+        conv_tf = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
+        pl_gbs = pl_bytes / (pl_ms * 1e-3) / 1e9
+        roofline = {"kernel": "conv implicit-GEMM family (fwd+dgrad+wgrad), %d launches/step" % conv_n,
+                    "bound": "tensor", "achieved": conv_tf, "peak": pk["tf"], "unit": "TFLOP/s",
+                    "frac": conv_tf / pk["tf"], "traffic": None, "peak_source": pk["src"],
+                    "ms_per_step": conv_ms, "share_of_step": conv_ms / ms}
+        roofline_loss = {"kernel": "fd_photoloss_fwd+bwd (4 launches/step)", "bound": "hbm",
+                         "achieved": pl_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": pl_gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                         "ms_per_step": pl_ms, "share_of_step": pl_ms / ms}
+        result = {
+            "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "trainer.py step (enc/dec/pose fwd+bwd + reprojection loss + Adam), "
+                                   "ResNet-18, 640x192, batch 12 per GPU = 2 micro-batches of 6",
+                       "cuda_graph": not args.no_graph, "parallelism": "dp%d" % world,
+                       "l2": "no explicit flush: each step streams >2 GB of activations (>> 126 MB L2)"},
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "clocks": clocks, "roofline": roofline, "roofline_loss": roofline_loss,
+            "loss_first": first_loss, "loss": float(loss),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline_leg()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if result is not None:
+        print(json.dumps(result))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--profile-step", dest="profile_step", action="store_true",
+                    help="run ONE eager optimiser step between cudaProfilerStart/Stop (for ncu "
+                         "--profile-from-start off) and exit; prints no bench line")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,30 @@ ACT = {"none": 0, "relu": 1, "elu": 2, "sigmoid": 3, "tanh": 4}
 CL = torch.channels_last
 
 
+# Optional per-kernel-family timing (bench.py's roofline leg): when PROFILE is a dict, every
+# timed call appends (start_event, end_event, algorithmic_work) under its family name.  Events are
+# recorded on the launching stream; nothing is synchronised here.
+PROFILE: Optional[Dict] = None
+
+
+class _timed:
+    def __init__(self, name: str, work: float):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            PROFILE.setdefault(self.name, []).append((self.s, e, self.work))
+        return False
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else c_void_p(t.data_ptr())
 
@@ -82,8 +106,9 @@ class Conv2dFn(torch.autograd.Function):
         Ho = (H + 2 * pad - KH) // stride + 1
         Wo = (W + 2 * pad - KW) // stride + 1
         y = empty_nhwc(B, Cout, Ho, Wo, x.device)
-        _lib.check(lib.fd_conv2d_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, Cout, KH, KW,
-                                     stride, pad, act, _stream()), "fd_conv2d_fwd")
+        with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
+            _lib.check(lib.fd_conv2d_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, Cout, KH, KW,
+                                         stride, pad, act, _stream()), "fd_conv2d_fwd")
         ctx.save_for_backward(x, w, y if act != 0 else None)
         ctx.cfg = (stride, pad, act, bias is not None)
         return y
@@ -111,14 +136,16 @@ class Conv2dFn(torch.autograd.Function):
             _lib.check(lib.fd_weight_transpose(_p(w), _p(wt), Cout, KH * KW, Cin, st),
                        "fd_weight_transpose")
             dx = empty_nhwc(B, Cin, H, W, x.device)
-            _lib.check(lib.fd_conv2d_dgrad(_p(dy), _p(wt), _p(dx), B, H, W, Cin, Cout, KH, KW, stride,
-                                           pad, st), "fd_conv2d_dgrad")
+            with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
+                _lib.check(lib.fd_conv2d_dgrad(_p(dy), _p(wt), _p(dx), B, H, W, Cin, Cout, KH, KW,
+                                               stride, pad, st), "fd_conv2d_dgrad")
         dw = None
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32,
-                             memory_format=CL)
-            _lib.check(lib.fd_conv2d_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW, stride,
-                                           pad, st), "fd_conv2d_wgrad")
+            dw = torch.empty((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32,
+                             memory_format=CL).zero_()
+            with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
+                _lib.check(lib.fd_conv2d_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
+                                               stride, pad, st), "fd_conv2d_wgrad")
         return dx, dw, dbias, None, None, None
 
 
@@ -384,8 +411,9 @@ class PhotoLossFn(torch.autograd.Function):
             outs["sel"] = sel
         ws = torch.empty(lib.fd_photoloss_workspace_bytes(B, H, W) // 4, device=dev, dtype=torch.float32)
         losses = torch.empty(9, device=dev, dtype=torch.float32)
-        _lib.check(lib.fd_photoloss_fwd(ctypes.byref(desc), _p(losses), _p(ws), _stream()),
-                   "fd_photoloss_fwd")
+        with _timed("photoloss_fwd", 213.25 * B * H * W):
+            _lib.check(lib.fd_photoloss_fwd(ctypes.byref(desc), _p(losses), _p(ws), _stream()),
+                       "fd_photoloss_fwd")
         # the forward-only outputs must not be rewritten by the backward's descriptor
         for s in range(4):
             desc.out_depth[s] = None
@@ -406,8 +434,9 @@ class PhotoLossFn(torch.autograd.Function):
         gT0 = torch.empty((B, 4, 4), device=dev, dtype=torch.float32)
         gT1 = torch.empty((B, 4, 4), device=dev, dtype=torch.float32)
         arr = (c_void_p * 4)(*[t.data_ptr() for t in gd])
-        _lib.check(lib.fd_photoloss_bwd(ctypes.byref(ctx.desc), _p(g), ctypes.byref(arr), _p(gT0),
-                                        _p(gT1), _p(ctx.ws), _stream()), "fd_photoloss_bwd")
+        with _timed("photoloss_bwd", 218.56 * B * H * W):
+            _lib.check(lib.fd_photoloss_bwd(ctypes.byref(ctx.desc), _p(g), ctypes.byref(arr), _p(gT0),
+                                            _p(gT1), _p(ctx.ws), _stream()), "fd_photoloss_bwd")
         return gd[0], gd[1], gd[2], gd[3], gT0, gT1, None, None, None
 
 

@@ -140,11 +140,11 @@ def _coherent_frames(B, H, W, g):
 def make_batch(B: int, H: int, W: int, seed: int = 1,
                lidar_fn: Optional[Callable[[np.ndarray], Dict[str, torch.Tensor]]] = None,
                frame_ids=(0, -1, 1), scales=(0, 1, 2, 3), mode: str = "uniform",
-               with_noise: bool = True) -> Dict:
+               with_noise: bool = True, lidar_density: float = 0.02) -> Dict:
     """One micro-batch keyed like the reference loader's output, all CPU fp32.
 
     ``lidar_fn(points[n,4] float32) -> {"4beam": [1,H,W], "2channel": [2,H,W]}``; when it
-    is None a Bernoulli(0.02) stand-in is used (speed-only runs).
+    is None a Bernoulli(lidar_density) stand-in is used (speed-only runs).
     ``noise[s]`` ([B,2,H,W] standard normal from the CPU generator) is what the reference
     draws at trainer.py:551 for the auto-mask tie-break.
     """
@@ -170,7 +170,7 @@ def make_batch(B: int, H: int, W: int, seed: int = 1,
                 m = lidar_fn(make_scan(seed * 1000 + b * 7 + (f + 1)))
                 fb, tc = m["4beam"], m["2channel"]
             else:
-                mask = (torch.rand(1, H, W, generator=g) < 0.02).float()
+                mask = (torch.rand(1, H, W, generator=g) < lidar_density).float()
                 fb = mask * (0.03 + 0.05 * torch.rand(1, H, W, generator=g))
                 tc = torch.cat([fb, mask], 0)
             two[f].append(tc.float().cpu())

@@ -143,12 +143,15 @@ class FlatParams:
     the data-parallel gradient exchange is one all-reduce and Adam is one kernel.  Conv weights
     keep their channels-last storage order inside the buffer."""
 
+    ALIGN = 64      # floats: every parameter starts on a 256 B boundary (float4 / TMA loads)
+
     def __init__(self, models: Dict[str, nn.Module]):
         params: List[nn.Parameter] = []
         for name in models:
             params += [p for p in models[name].parameters() if p.requires_grad]
         self.params = params
-        n = sum(p.numel() for p in params)
+        A = self.ALIGN
+        n = sum((p.numel() + A - 1) // A * A for p in params)
         dev = params[0].device
         self.data = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -159,7 +162,7 @@ class FlatParams:
             dv.copy_(p.data)
             p.data = dv
             p.grad = gv
-            off += k
+            off += (k + A - 1) // A * A
         self.numel = n
 
     @staticmethod

@@ -22,7 +22,9 @@ def _seed_of(key: str, seed: int) -> int:
 def synth_weights(template: "OrderedDict[str, torch.Tensor]", seed: int = 0):
     """Deterministic weights for a state_dict *template* (only key -> shape/dtype is used),
     independent of module construction order: every tensor is drawn from its own generator
-    seeded by hash(seed, key).  Conv/linear weights ~ N(0, 2/fan_out); BN weight ~ U(.5,1.5);
+    seeded by hash(seed, key).  Conv/linear weights ~ N(0, 1/fan_in) (unit gain, so that the
+    activations -- and the sigmoid logits -- stay O(1) and the nets are well conditioned in both
+    train and eval mode); BN weight ~ U(.5,1.5);
     biases, running_mean ~ small normal; running_var ~ U(.5,1.5)."""
     out = OrderedDict()
     for k, t in template.items():
@@ -34,8 +36,8 @@ def synth_weights(template: "OrderedDict[str, torch.Tensor]", seed: int = 0):
         elif k.endswith("running_mean"):
             out[k] = 0.1 * torch.randn(t.shape, generator=g)
         elif t.dim() >= 2:
-            fan_out = t.shape[0] * int(np.prod(t.shape[2:])) if t.dim() == 4 else t.shape[0]
-            out[k] = torch.randn(t.shape, generator=g) * float(np.sqrt(2.0 / fan_out))
+            fan_in = int(np.prod(t.shape[1:]))
+            out[k] = torch.randn(t.shape, generator=g) * float(np.sqrt(1.0 / fan_in))
         elif ".bn" in k or "downsample.1" in k:
             out[k] = (0.5 + torch.rand(t.shape, generator=g)) if k.endswith("weight") \
                 else 0.1 * torch.randn(t.shape, generator=g)

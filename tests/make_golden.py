@@ -72,14 +72,14 @@ def _load_weights(models, seed):
         m.load_state_dict(synth_weights(m.state_dict(), seed * 100 + i))
 
 
-def gen_step(ns, B=2, H=64, W=96):
+def gen_step(ns, B=3, H=96, W=160):
     """Full Trainer.process_batch + backward (config 2 semantics at a small size)."""
     models = RH.make_models(ns, 18)
     _load_weights(models, 0)
     for m in models.values():
         m.train()
     tr = RH.make_trainer(ns, models, B, H, W)
-    inputs = synth.make_batch(B, H, W, seed=1)
+    inputs = synth.make_batch(B, H, W, seed=1, mode="coherent", lidar_density=0.25)
     noise = inputs.pop("noise")
     with RH.FixedNoise([noise[s] for s in range(4)]):
         outputs, losses = tr.process_batch(dict(inputs))

@@ -1,0 +1,159 @@
+"""Network operators (CUDA) vs plain PyTorch fp32 on the CPU (same op, autograd for backward)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests._util import rel_err
+
+pytestmark = pytest.mark.gpu
+CL = torch.channels_last
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+CONV_CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad, bias, act
+    (2, 3, 32, 48, 64, 7, 2, 3, False, "none"),      # stem, scalar path
+    (2, 6, 32, 48, 64, 7, 2, 3, False, "none"),
+    (2, 64, 16, 24, 64, 3, 1, 1, False, "none"),     # layer1
+    (2, 64, 16, 24, 128, 3, 2, 1, False, "none"),    # strided
+    (2, 64, 16, 24, 128, 1, 2, 0, False, "none"),    # downsample
+    (3, 128, 9, 13, 256, 3, 1, 1, True, "relu"),     # ragged M
+    (2, 32, 18, 26, 16, 3, 1, 0, True, "elu"),       # decoder (valid conv on padded input)
+    (2, 16, 34, 50, 1, 3, 1, 0, True, "sigmoid"),    # disparity head, Cout=1
+    (1, 22, 20, 28, 22, 3, 1, 0, True, "elu"),       # refine decoder odd channels
+    (2, 256, 4, 6, 12, 1, 1, 0, True, "none"),       # pose head
+    (2, 48, 10, 14, 40, 3, 1, 1, True, "tanh"),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fwd_bwd(cuda, case):
+    from fusiondepth_b200 import ops
+    B, Cin, H, W, Cout, k, s, p, bias, act = case
+    x = _rand((B, Cin, H, W), 1)
+    w = _rand((Cout, Cin, k, k), 2, (2.0 / (Cin * k * k)) ** 0.5)
+    b = _rand((Cout,), 3, 0.1) if bias else None
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if bias else None
+    y = F.conv2d(xr, wr, br, s, p)
+    y = {"none": lambda t: t, "relu": F.relu, "elu": F.elu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](y)
+    gy = _rand(tuple(y.shape), 4)
+    y.backward(gy)
+    xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    wc = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    bc = b.cuda().requires_grad_(True) if bias else None
+    yc = ops.conv2d(xc, wc, bc, s, p, act)
+    yc.backward(gy.cuda())
+    assert yc.shape == y.shape
+    assert rel_err(yc.detach().cpu(), y.detach()) < 2e-5
+    assert rel_err(xc.grad.cpu(), xr.grad) < 2e-5
+    assert rel_err(wc.grad.cpu(), wr.grad) < 5e-5
+    if bias:
+        assert rel_err(bc.grad.cpu(), br.grad) < 5e-5
+
+
+@pytest.mark.parametrize("C,relu,res,training", [(64, True, False, True), (128, True, True, True),
+                                                 (20, False, False, True), (64, True, True, False)])
+def test_batch_norm(cuda, C, relu, res, training):
+    from fusiondepth_b200 import ops
+    B, H, W = 3, 10, 14
+    x = _rand((B, C, H, W), 1) * 2 + 0.5
+    r = _rand((B, C, H, W), 2) if res else None
+    gamma, beta = 0.5 + torch.rand(C, generator=torch.Generator().manual_seed(3)), _rand((C,), 4, 0.1)
+    rm, rv = _rand((C,), 5, 0.1), 0.5 + torch.rand(C, generator=torch.Generator().manual_seed(6))
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rr = r.clone().requires_grad_(True) if res else None
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y = F.batch_norm(xr, rm_ref, rv_ref, gr, br, training, 0.1, 1e-5)
+    if res:
+        y = y + rr
+    if relu:
+        y = F.relu(y)
+    gy = _rand(tuple(y.shape), 7)
+    y.backward(gy)
+    xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    gc, bc = gamma.cuda().requires_grad_(True), beta.cuda().requires_grad_(True)
+    rc = r.cuda().contiguous(memory_format=CL).requires_grad_(True) if res else None
+    rmc, rvc = rm.cuda(), rv.cuda()
+    yc = ops.batch_norm(xc, gc, bc, rmc, rvc, rc, training, 0.1, 1e-5, relu)
+    yc.backward(gy.cuda())
+    assert rel_err(yc.detach().cpu(), y.detach()) < 1e-5
+    assert rel_err(xc.grad.cpu(), xr.grad) < 5e-5
+    assert rel_err(gc.grad.cpu(), gr.grad) < 5e-5
+    assert rel_err(bc.grad.cpu(), br.grad) < 5e-5
+    if res:
+        assert rel_err(rc.grad.cpu(), rr.grad) < 1e-6
+    assert rel_err(rmc.cpu(), rm_ref) < 1e-6 and rel_err(rvc.cpu(), rv_ref) < 1e-5
+
+
+def test_maxpool(cuda):
+    from fusiondepth_b200 import ops
+    x = F.relu(_rand((2, 64, 17, 24), 1))            # ReLU output: many exact-zero ties
+    xr = x.clone().requires_grad_(True)
+    y = F.max_pool2d(xr, 3, 2, 1)
+    gy = _rand(tuple(y.shape), 2)
+    y.backward(gy)
+    xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    yc = ops.maxpool3x3s2(xc)
+    yc.backward(gy.cuda())
+    assert torch.equal(yc.detach().cpu(), y.detach())
+    # ties between zeros may route differently but ReLU kills them; compare where x > 0
+    m = x > 0
+    assert rel_err((xc.grad.cpu() * m), (xr.grad * m)) < 1e-6
+
+
+def test_assemble(cuda):
+    from fusiondepth_b200 import ops
+    B, H, W = 2, 12, 16
+    a = _rand((B, 32, H // 2, W // 2), 1)
+    s1, s2 = _rand((B, 24, H, W), 2), _rand((B, 24, H, W), 3)
+    e = _rand((B, 6, H, W), 4)
+    leaves = [t.clone().requires_grad_(True) for t in (a, s1, s2, e)]
+    cat = torch.cat([F.interpolate(leaves[0], scale_factor=2, mode="nearest"), leaves[1] + leaves[2], leaves[3]], 1)
+    y = F.pad(cat, (1, 1, 1, 1), mode="reflect")
+    gy = _rand(tuple(y.shape), 5)
+    y.backward(gy)
+    cl = [t.cuda().contiguous(memory_format=CL).requires_grad_(True) for t in (a, s1, s2, e)]
+    yc = ops.assemble([(cl[0], None, True), (cl[1], cl[2], False), (cl[3], None, False)], pad=1)
+    yc.backward(gy.cuda())
+    assert torch.equal(yc.detach().cpu(), y.detach())
+    for c, r in zip(cl, leaves):
+        assert rel_err(c.grad.cpu(), r.grad) < 1e-6
+
+
+def test_prep_mean_add(cuda):
+    from fusiondepth_b200 import ops
+    x = torch.rand(2, 3, 8, 12, generator=torch.Generator().manual_seed(1))
+    y = ops.prep_input(x.cuda())
+    assert torch.equal(y.cpu(), ((x - 0.45) / 0.225))
+    z = _rand((2, 12, 6, 20), 2)
+    zc = z.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    m = ops.mean_hw(zc, 0.01)
+    m.sum().backward()
+    assert rel_err(m.detach().cpu(), 0.01 * z.mean(3).mean(2)) < 1e-6
+    assert rel_err(zc.grad.cpu(), torch.full_like(z, 0.01 / 120)) < 1e-6
+    a, b = _rand((2, 8, 4, 4), 3).cuda(), _rand((2, 8, 4, 4), 4).cuda()
+    assert torch.equal(ops.add(a, b), a + b)
+
+
+def test_adam_matches_torch(cuda):
+    from fusiondepth_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(100003, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], 1e-3)
+    p = p0.cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.zeros(4, dtype=torch.int32, device="cuda")
+    for _ in range(5):
+        gr = torch.randn(100003, generator=g)
+        ref.grad = gr.clone()
+        opt.step()
+        ops.adam_step(p, gr.cuda(), m, v, state, 1e-3)
+    assert int(state[0]) == 5
+    assert rel_err(p.cpu(), ref.detach()) < 1e-6

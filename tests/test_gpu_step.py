@@ -1,0 +1,161 @@
+"""Networks and the full training step (CUDA) vs reference fixtures and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import GOLDEN, clone_sd, rel_err, synth_weights
+from fusiondepth_b200 import synth
+from oracle import step_oracle as SO
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(models, seed):
+    sds = {}
+    for i, (name, m) in enumerate(sorted(models.items())):
+        sds[name] = synth_weights(m.state_dict(), seed * 100 + i)
+        m.load_state_dict(sds[name])
+    return sds
+
+
+def test_forward_variants_vs_reference_fixture(cuda):
+    from fusiondepth_b200 import networks
+    g = np.load(GOLDEN + "/forward_variants.npz")
+    rgb, two = torch.from_numpy(g["rgb"]).cuda(), torch.from_numpy(g["two"]).cuda()
+    for nl in (18, 50):
+        enc = networks.ResnetEncoder(nl, False)
+        benc = networks.ResnetEncoder(nl, False, beam_encoder=True)
+        dec = networks.DepthDecoder(enc.num_ch_enc, [0, 1, 2, 3])
+        for i, m in enumerate((enc, benc, dec)):
+            m.load_state_dict(synth_weights(m.state_dict(), 1000 + nl * 10 + i))
+            m.cuda().eval()
+        with torch.no_grad():
+            f, b = enc(rgb), benc(two)
+            f = list(f)
+            d = dec(f, beam_features=b)
+        assert rel_err(f[4].cpu(), g["r%d/feat4" % nl]) < 1e-4
+        for s in range(4):
+            assert rel_err(d[("disp", s)].cpu(), g["r%d/disp%d" % (nl, s)]) < 1e-4
+        if nl == 18:
+            r2d = networks.DepthDecoder(enc.num_ch_enc, [0, 1, 2, 3], road=True, catxy=True, deep=True)
+            r2d.load_state_dict(synth_weights(r2d.state_dict(), 2000))
+            r2d.cuda().eval()
+            dm = {("disp", s): torch.from_numpy(g["refine/dm%d" % s]).cuda() for s in range(4)}
+            with torch.no_grad():
+                r = r2d(f, beam_features=b, depth_maps=dm, tanh=False)
+            for s in range(4):
+                assert rel_err(r[("disp", s)].cpu(), g["refine/disp%d" % s]) < 1e-4
+    pc = networks.PoseCNN(2)
+    pc.load_state_dict(synth_weights(pc.state_dict(), 3000))
+    pc.cuda()
+    with torch.no_grad():
+        aa, tt = pc(torch.cat([rgb, rgb.flip(3)], 1))
+    assert rel_err(aa.cpu(), g["posecnn/aa"]) < 1e-4 and rel_err(tt.cpu(), g["posecnn/t"]) < 1e-4
+
+
+def test_train_step_vs_reference_fixture(cuda):
+    """Trainer.process_batch + backward at B=3, 96x160: losses, disparities, poses, every
+    parameter-gradient norm and every BN running statistic against the reference's values."""
+    from fusiondepth_b200 import training
+    g = np.load(GOLDEN + "/step_r18.npz")
+    models = training.build_models(18, "cuda")
+    _load(models, 0)
+    for m in models.values():
+        m.train()
+    inputs = synth.make_batch(3, 96, 160, seed=1, mode="coherent", lidar_density=0.25)
+    noise = {s: t.cuda() for s, t in inputs.pop("noise").items()}
+    inputs = synth.to_device(inputs, "cuda")
+    outputs, losses = training.process_batch(models, inputs, noise, None, materialize=True)
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+    for k in losses:
+        assert rel_err(losses[k].detach().cpu(), g["loss:" + k]) < 1e-4, (k, float(losses[k]), float(g["loss:" + k]))
+    for s in range(4):
+        assert rel_err(outputs[("disp", s)].detach().cpu(), g["disp%d" % s]) < 1e-4, s
+        assert rel_err(outputs[("depth", 0, s)].detach().cpu(), g["depth%d" % s]) < 1e-4, s
+    for f in (-1, 1):
+        assert rel_err(outputs[("cam_T_cam", 0, f)].detach().cpu(), g["cam_T_cam%d" % f]) < 1e-5
+        assert rel_err(outputs[("color", f, 0)].detach().cpu(), g["color%d_0" % f]) < 2e-4
+    bad = []
+    n = 0
+    for key in g.files:
+        if key.startswith("gnorm:"):
+            name, pk = key[6:].split("/", 1)
+            p = dict(models[name].named_parameters())[pk]
+            assert p.grad is not None, key
+            got, want = float(p.grad.double().norm()), float(g[key])
+            n += 1
+            if abs(got - want) > 5e-3 * want + 1e-9:
+                bad.append((key, got, want))
+        elif key.startswith("buf:"):
+            name, pk = key[4:].split("/", 1)
+            b = dict(models[name].named_buffers())[pk]
+            got, want = float(b.double().norm()), float(g[key])
+            if abs(got - want) > 1e-4 * want + 1e-9:
+                bad.append((key, got, want))
+    assert n > 200 and not bad, bad[:10]
+    assert rel_err(models["encoder"].encoder.conv1.weight.grad.cpu(), g["grad:encoder/conv1"]) < 5e-3
+
+
+def test_train_step_vs_oracle_and_adam(cuda):
+    """one full optimiser step (2 micro-batches, accumulate) vs the oracle: loss and updated weights"""
+    from fusiondepth_b200 import training
+    models = training.build_models(18, "cuda")
+    sds = _load(models, 3)
+    osd = {k: clone_sd(v, requires_grad=True) for k, v in sds.items()}
+    batches = [synth.make_batch(2, 96, 128, seed=10 + i, mode="coherent", lidar_density=0.25) for i in range(2)]
+    noises = [b.pop("noise") for b in batches]
+    # oracle
+    tot = 0
+    for b, nz in zip(batches, noises):
+        _, l = SO.process_batch(osd, b, nz, 18, training=True)
+        (l["loss"] / 2).backward()
+        tot += float(l["loss"]) / 2
+    step = training.TrainStep(models, lr=1e-4, accumulate=2)
+    cb = [synth.to_device(b, "cuda") for b in batches]
+    cn = [{s: t.cuda() for s, t in nz.items()} for nz in noises]
+    loss = step.step(cb, cn)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - tot) < 1e-4 * abs(tot)
+    # compare the gradient of a few tensors and the Adam-updated weights
+    for name, key in (("depth", "decoder.0.conv.conv.weight"), ("pose", "net.3.weight"),
+                      ("encoder", "encoder.layer1.0.conv1.weight"), ("beam_encoder_pose", "encoder.conv1.weight")):
+        p = dict(models[name].named_parameters())[key]
+        assert rel_err(p.grad.cpu(), osd[name][key].grad) < 5e-3, (name, key)
+    params, grads = [], []
+    for name in models:
+        for k, p in models[name].named_parameters():
+            if osd[name][k].grad is not None:
+                params.append((p, osd[name][k]))
+    ps = [o.detach().clone() for _, o in params]
+    SO.adam_step(ps, [o.grad for _, o in params], [torch.zeros_like(x) for x in ps],
+                 [torch.zeros_like(x) for x in ps], 1, 1e-4)
+    # first Adam step moves every weight by ~lr * sign(grad): compare the update direction
+    agree = tot_n = 0
+    for (p, o), pn in zip(params, ps):
+        du_ref = (pn - o.detach())
+        du = (p.detach().cpu() - o.detach())
+        big = o.grad.abs() > 1e-6 * o.grad.abs().max()
+        agree += int((torch.sign(du[big]) == torch.sign(du_ref[big])).sum())
+        tot_n += int(big.sum())
+    assert agree / tot_n > 0.999
+
+
+def test_cuda_graph_replay_matches_eager(cuda):
+    from fusiondepth_b200 import training
+    torch.manual_seed(0)
+    models = training.build_models(18, "cuda")
+    _load(models, 5)
+    batches = [synth.to_device(synth.make_batch(2, 64, 96, seed=20, with_noise=False), "cuda")]
+    noises = [{s: torch.randn(2, 2, 64, 96, device="cuda") for s in range(4)}]
+    step = training.TrainStep(models, lr=1e-4, accumulate=1)
+    step.capture(batches, noises)
+    w0 = step.flat.data.clone()
+    l_graph = float(step.replay())
+    w_graph = step.flat.data.clone()
+    # eager from the same starting point
+    step.flat.data.copy_(w0)
+    step.exp_avg.zero_(); step.exp_avg_sq.zero_(); step.adam_state.zero_()
+    l_eager = float(step.step(batches, noises))
+    assert abs(l_graph - l_eager) < 1e-5 * abs(l_eager)
+    assert rel_err(w_graph.cpu(), step.flat.data.cpu()) < 1e-5

@@ -75,7 +75,7 @@ def _models_sd(seed=0, num_layers=18):
 def test_step_oracle_matches_reference_fixture():
     g = _g("step_r18")
     sds = {k: clone_sd(v, requires_grad=True) for k, v in _models_sd(0).items()}
-    inputs = synth.make_batch(2, 64, 96, seed=1)
+    inputs = synth.make_batch(3, 96, 160, seed=1, mode="coherent", lidar_density=0.25)
     noise = inputs.pop("noise")
     outputs, losses = SO.process_batch(sds, inputs, noise, 18, training=True)
     losses["loss"].backward()
