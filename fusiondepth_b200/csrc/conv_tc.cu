@@ -1,0 +1,496 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / TMEM), forward and data
+// gradient, at fp32 accuracy through error-compensated TF32 splitting ("3xTF32").
+//
+// Replaces aten::convolution / convolution_backward(input) under networks/* for every layer whose
+// gathered channel count is a multiple of 32 and whose output channel count is a multiple of 16
+// (all ResNet trunk 3x3/1x1 convs and most decoder convs); conv.cu keeps the rest.
+//
+// GEMM view (NHWC activations, weights [N][taps*Cg] K-major):
+//     D[m][n] = sum_k A[m][k] * B[n][k],   m = output pixel, k = (tap, channel)
+// CTA tile 128 (pixels) x BN (channels), K step 32 floats = one 128-byte swizzle row.
+//
+// Roles (288 threads, one CTA per SM):
+//   warps 0-3  loaders: gather the im2col rows of A straight from global memory into a
+//              SWIZZLE_128B shared-memory tile with cp.async (zero-fill = padding); one elected
+//              thread fetches the two weight tiles (W, W_lo) with TMA (cp.async.bulk.tensor.2d);
+//              both complete on the stage's `landed` mbarrier;
+//   warps 4-7  splitters: derive the low-order tile A_lo = A - tf32(A) in shared memory, then
+//              (after the K loop) run the epilogue: tcgen05.ld the accumulators (one pixel row per
+//              thread), bias + activation, vectorised NHWC stores;
+//   warp 8     one elected thread issues tcgen05.mma.kind::tf32 (the tensor core reads the top
+//              19 bits of each fp32 word, so feeding the raw fp32 tile *is* feeding tf32(A)):
+//                  corr  += A_lo*B + A*B_lo          (one TMEM accumulator)
+//                  main_i += A*B                      (round-robin over up to 7 TMEM accumulators)
+//              The tensor core truncates when it adds into an fp32 accumulator, which biases long
+//              K reductions (measured 3e-5 at K = 4608 with one accumulator); keeping the tiny
+//              correction terms apart and spreading the main products over several accumulators
+//              that the epilogue sums with round-to-nearest adds restores fp32-level accuracy.
+// Stage hand-off is mbarrier based (landed: cp.async + TMA tx; full: 128 splitter arrivals;
+// empty / accumulator-ready: tcgen05.commit).  W_lo = W - tf32(W) comes from fd_tf32_split.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/fusiondepth_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BK = 32;
+constexpr int NPROD = 128, NTHREADS = 288;
+constexpr int A_TILE = BM * 128;   // bytes
+
+struct TcArgs {
+  const float* x;     // gathered tensor [B,Hg,Wg,Cg]
+  const float* w;     // [N][K] raw fp32
+  const float* wlo;   // [N][K] low-order part
+  const float* bias;
+  float* y;           // [M][N]
+  int B, Hg, Wg, Cg, Ho, Wo, N, KH, KW, stride, pad, act;
+  long M;
+  int K;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 28)) __trap();   // never hang the device on a protocol error
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+  switch (act) {
+    case FD_ACT_RELU: return fmaxf(v, 0.f);
+    case FD_ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case FD_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case FD_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&o)[16]) {
+  uint32_t v[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < 16; ++q) o[q] = __uint_as_float(v[q]);
+}
+__device__ __forceinline__ float lo_part(float v) {
+  return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  // TMEM: accumulator 0 = correction terms, 1..NMAIN = main products (round robin)
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 512 : (BN == 32 ? 256 : 128));
+  static constexpr int NMAIN = TMEM_COLS / BN - 1 > 7 ? 7 : TMEM_COLS / BN - 1;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// MODE 0: forward conv.  MODE 1: data gradient (x = dy, w = transposed weights).
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + C::STAGES * C::STAGE;
+  auto landed_bar = [&](int s) { return bars + 8u * s; };
+  auto full_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  const uint32_t acc_bar = bars + 8u * (3 * C::STAGES);
+  const uint32_t tmem_slot = acc_bar + 8u;
+  auto a_raw = [&](int s) { return base + s * C::STAGE; };
+  auto a_lo = [&](int s) { return base + s * C::STAGE + A_TILE; };
+  auto b_raw = [&](int s) { return base + s * C::STAGE + 2 * A_TILE; };
+  auto b_lo = [&](int s) { return base + s * C::STAGE + 2 * A_TILE + C::B_TILE; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long m0 = (long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int nk = a.K / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed_bar(s), NPROD + 1);   // 128 cp.async completions + 1 expect_tx arrive
+      mbar_init(full_bar(s), NPROD);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wlo) : "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    // ======================= loaders =======================
+    const int j = tid & 7, rg = tid >> 3;
+    int hb[8], wb[8];
+    long pb[8];
+    const int HoWo = a.Ho * a.Wo;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      long m = m0 + rg + 16 * i;
+      if (m < a.M) {
+        int b = (int)(m / HoWo), r = (int)(m % HoWo);
+        int ho = r / a.Wo, wo = r % a.Wo;
+        hb[i] = MODE == 0 ? ho * a.stride - a.pad : ho + a.pad;
+        wb[i] = MODE == 0 ? wo * a.stride - a.pad : wo + a.pad;
+        pb[i] = (long)b * a.Hg * a.Wg;
+      } else {
+        hb[i] = -(1 << 28); wb[i] = 0; pb[i] = 0;
+      }
+    }
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % C::STAGES;
+      if (it >= C::STAGES) mbar_wait(empty_bar(s), ((it / C::STAGES) - 1) & 1);
+      const int k0 = it * BK;
+      if (tid == 0) {
+        mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
+        tma_load_2d(b_raw(s), &tm_w, k0, n0, landed_bar(s));
+        tma_load_2d(b_lo(s), &tm_wlo, k0, n0, landed_bar(s));
+      }
+      const int tap = k0 / a.Cg, c0 = k0 - tap * a.Cg;
+      const int kh = tap / a.KW, kw = tap - kh * a.KW;
+      const uint32_t ar = a_raw(s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rg + 16 * i;
+        int h, w;
+        bool ok;
+        if (MODE == 0) {
+          h = hb[i] + kh; w = wb[i] + kw;
+          ok = h >= 0 && h < a.Hg && w >= 0 && w < a.Wg;
+        } else {
+          int th = hb[i] - kh, tw = wb[i] - kw;
+          ok = th >= 0 && tw >= 0;
+          if (a.stride > 1) {
+            ok = ok && (th % a.stride == 0) && (tw % a.stride == 0);
+            th /= a.stride; tw /= a.stride;
+          }
+          h = th; w = tw;
+          ok = ok && h < a.Hg && w < a.Wg;
+        }
+        const float* src = ok ? a.x + ((pb[i] + (long)h * a.Wg + w) * a.Cg + c0 + j * 4) : a.x;
+        cp_async16(ar + r * 128 + ((j ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+      }
+      cp_async_arrive_noinc(landed_bar(s));
+    }
+  } else if (warp < 8) {
+    // ======================= splitters, then epilogue =======================
+    const int t = tid - 128;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % C::STAGES;
+      mbar_wait(landed_bar(s), (it / C::STAGES) & 1);
+      const uint32_t ar = a_raw(s), al = a_lo(s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t so = (uint32_t)(t + 128 * i) * 16u;   // the split is elementwise: any mapping
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(ar + so));
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(al + so), "f"(lo_part(v.x)),
+                     "f"(lo_part(v.y)), "f"(lo_part(v.z)), "f"(lo_part(v.w))
+                     : "memory");
+      }
+      fence_async_proxy();
+      mbar_arrive(full_bar(s));
+    }
+    // ---- epilogue ----
+    const int ew = warp - 4;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const long m = m0 + ew * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
+    const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float acc[16], tmp[16];
+      tmem_ld16(trow + (uint32_t)(BN + c), acc);
+      for (int q = 1; q < nmain; ++q) {
+        tmem_ld16(trow + (uint32_t)((1 + q) * BN + c), tmp);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] += tmp[e];
+      }
+      tmem_ld16(trow + (uint32_t)c, tmp);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] += tmp[e];
+      if (m < a.M && n0 + c < a.N) {
+        float o[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float bv = a.bias ? a.bias[n0 + c + q] : 0.f;
+          o[q] = act_fn(acc[q] + bv, a.act);
+        }
+        float4* dst = reinterpret_cast<float4*>(a.y + m * a.N + n0 + c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    }
+  } else {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % C::STAGES;
+        mbar_wait(full_bar(s), (kb / C::STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = make_desc(a_raw(s)), dal = make_desc(a_lo(s));
+        const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
+        const uint32_t d_corr = tmem_base;
+        const uint32_t d_main = tmem_base + (uint32_t)((1 + kb % C::NMAIN) * BN);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);
+          umma_tf32(d_corr, dal + adv, db + adv, idesc, (kb | k) != 0);
+          umma_tf32(d_corr, da + adv, dbl + adv, idesc, 1);
+          umma_tf32(d_main, da + adv, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(acc_bar);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+__global__ void tf32_split_kernel(const float* __restrict__ w, float* __restrict__ lo, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = w[i];
+    lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+}
+
+// w [Cout][taps][Cin] -> wt [Cin][taps][Cout] and its low-order part
+__global__ void transpose_split_kernel(const float* __restrict__ w, float* __restrict__ wt,
+                                       float* __restrict__ wtlo, int Cout, int taps, int Cin) {
+  long n = (long)Cout * taps * Cin;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int co = i % Cout;
+    int tp = (i / Cout) % taps;
+    int ci = i / ((long)Cout * taps);
+    float v = w[((long)co * taps + tp) * Cin + ci];
+    wt[i] = v;
+    wtlo[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+}
+
+
+// ---- host side: TMA descriptors for the weight tiles --------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows][cols] (cols contiguous), box = 32 cols x box_rows, SWIZZLE_128B
+int make_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  FD_REQUIRE(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld", (int)r,
+             rows, cols);
+  return 0;
+}
+
+template <int BN, int MODE>
+int launch_tc(const TcArgs& a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) {
+      fd::set_error("conv_tc: cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  CUtensorMap tw, twl;
+  int rc = make_map_2d(&tw, a.w, a.N, a.K, BN);
+  if (rc) return rc;
+  rc = make_map_2d(&twl, a.wlo, a.N, a.K, BN);
+  if (rc) return rc;
+  dim3 grid(fd::cdiv(a.M, BM), fd::cdiv(a.N, BN));
+  conv_tc_kernel<BN, MODE><<<grid, NTHREADS, C::SMEM, st>>>(a, tw, twl);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int MODE>
+int dispatch_tc(const TcArgs& a, cudaStream_t st) {
+  FD_REQUIRE((((uintptr_t)a.w | (uintptr_t)a.wlo | (uintptr_t)a.x) & 15) == 0,
+             "conv_tc: operands must be 16-byte aligned");
+  if (a.N % 128 == 0) return launch_tc<128, MODE>(a, st);
+  if (a.N % 64 == 0) return launch_tc<64, MODE>(a, st);
+  if (a.N % 32 == 0) return launch_tc<32, MODE>(a, st);
+  return launch_tc<16, MODE>(a, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fd_conv2d_tc_supported(int Cin, int Cout) { return (Cin % 32 == 0) && (Cout % 16 == 0); }
+
+int fd_tf32_split(const float* w, float* w_lo, long n, void* stream) {
+  tf32_split_kernel<<<min(fd::cdiv(n, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, w_lo, n);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_weight_transpose_split(const float* w, float* wt, float* wt_lo, int Cout, int taps, int Cin,
+                              void* stream) {
+  long n = (long)Cout * taps * Cin;
+  transpose_split_kernel<<<min(fd::cdiv(n, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      w, wt, wt_lo, Cout, taps, Cin);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_conv2d_fwd_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                     int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                     int act, void* stream) {
+  FD_REQUIRE(fd_conv2d_tc_supported(Cin, Cout),
+             "fd_conv2d_fwd_tc: needs Cin %% 32 == 0 and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
+  TcArgs a;
+  a.x = x; a.w = w; a.wlo = w_lo; a.bias = bias; a.y = y;
+  a.B = B; a.Hg = H; a.Wg = W; a.Cg = Cin;
+  a.Ho = (H + 2 * pad - KH) / stride + 1;
+  a.Wo = (W + 2 * pad - KW) / stride + 1;
+  a.N = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.act = act;
+  a.M = (long)B * a.Ho * a.Wo;
+  a.K = KH * KW * Cin;
+  return dispatch_tc<0>(a, (cudaStream_t)stream);
+}
+
+int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, float* dx, int B, int H,
+                       int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream) {
+  FD_REQUIRE(fd_conv2d_tc_supported(Cout, Cin),
+             "fd_conv2d_dgrad_tc: needs Cout %% 32 == 0 and Cin %% 16 == 0 (got %d, %d)", Cout, Cin);
+  TcArgs a;
+  a.x = dy; a.w = wt; a.wlo = wt_lo; a.bias = nullptr; a.y = dx;
+  a.B = B;
+  a.Hg = (H + 2 * pad - KH) / stride + 1;
+  a.Wg = (W + 2 * pad - KW) / stride + 1;
+  a.Cg = Cout;
+  a.Ho = H; a.Wo = W; a.N = Cin;
+  a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.act = FD_ACT_NONE;
+  a.M = (long)B * H * W;
+  a.K = KH * KW * Cout;
+  return dispatch_tc<1>(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -7,6 +7,7 @@ weights are logical [Cout,Cin,KH,KW] stored channels-last ([Cout,KH,KW,Cin]).
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_int, c_void_p
 from typing import Dict, List, Optional, Sequence
 
@@ -15,6 +16,8 @@ import torch
 from . import _lib
 
 ACT = {"none": 0, "relu": 1, "elu": 2, "sigmoid": 3, "tanh": 4}
+# "tc": tcgen05 tensor-core convolutions wherever eligible (default); "cudacore": exact-fp32 path
+CONV_BACKEND = os.environ.get("FD_CONV", "tc")
 CL = torch.channels_last
 
 
@@ -106,9 +109,18 @@ class Conv2dFn(torch.autograd.Function):
         Ho = (H + 2 * pad - KH) // stride + 1
         Wo = (W + 2 * pad - KW) // stride + 1
         y = empty_nhwc(B, Cout, Ho, Wo, x.device)
-        with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
-            _lib.check(lib.fd_conv2d_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, Cout, KH, KW,
-                                         stride, pad, act, _stream()), "fd_conv2d_fwd")
+        use_tc = CONV_BACKEND == "tc" and Cin % 32 == 0 and Cout % 16 == 0
+        if use_tc:
+            wlo = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
+            _lib.check(lib.fd_tf32_split(_p(w), _p(wlo), w.numel(), _stream()), "fd_tf32_split")
+            with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
+                _lib.check(lib.fd_conv2d_fwd_tc(_p(x), _p(w), _p(wlo), _p(bias), _p(y), B, H, W, Cin,
+                                                Cout, KH, KW, stride, pad, act, _stream()),
+                           "fd_conv2d_fwd_tc")
+        else:
+            with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
+                _lib.check(lib.fd_conv2d_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, Cout, KH, KW,
+                                             stride, pad, act, _stream()), "fd_conv2d_fwd")
         ctx.save_for_backward(x, w, y if act != 0 else None)
         ctx.cfg = (stride, pad, act, bias is not None)
         return y
@@ -133,12 +145,20 @@ class Conv2dFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wt = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
-            _lib.check(lib.fd_weight_transpose(_p(w), _p(wt), Cout, KH * KW, Cin, st),
-                       "fd_weight_transpose")
             dx = empty_nhwc(B, Cin, H, W, x.device)
-            with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
-                _lib.check(lib.fd_conv2d_dgrad(_p(dy), _p(wt), _p(dx), B, H, W, Cin, Cout, KH, KW,
-                                               stride, pad, st), "fd_conv2d_dgrad")
+            if CONV_BACKEND == "tc" and Cout % 32 == 0 and Cin % 16 == 0:
+                wtlo = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
+                _lib.check(lib.fd_weight_transpose_split(_p(w), _p(wt), _p(wtlo), Cout, KH * KW, Cin, st),
+                           "fd_weight_transpose_split")
+                with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
+                    _lib.check(lib.fd_conv2d_dgrad_tc(_p(dy), _p(wt), _p(wtlo), _p(dx), B, H, W, Cin,
+                                                      Cout, KH, KW, stride, pad, st), "fd_conv2d_dgrad_tc")
+            else:
+                _lib.check(lib.fd_weight_transpose(_p(w), _p(wt), Cout, KH * KW, Cin, st),
+                           "fd_weight_transpose")
+                with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
+                    _lib.check(lib.fd_conv2d_dgrad(_p(dy), _p(wt), _p(dx), B, H, W, Cin, Cout, KH, KW,
+                                                   stride, pad, st), "fd_conv2d_dgrad")
         dw = None
         if ctx.needs_input_grad[1]:
             dw = torch.empty((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32,

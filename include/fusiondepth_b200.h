@@ -113,6 +113,20 @@ int fd_conv2d_dgrad(const float* dy, const float* wt, float* dx, int B, int H, i
 int fd_conv2d_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin,
                     int Cout, int KH, int KW, int stride, int pad, void* stream);
 int fd_weight_transpose(const float* w, float* wt, int Cout, int taps, int Cin, void* stream);
+
+/* Tensor-core path (tcgen05.mma kind::tf32, TMEM accumulators, 3xTF32 error-compensated split:
+ * fp32-level accuracy).  Eligible when the gathered channel count is a multiple of 32 and the
+ * produced channel count a multiple of 16 (fd_conv2d_tc_supported).  w_lo = w - tf32(w)
+ * (fd_tf32_split); for the data gradient wt / wt_lo come from fd_weight_transpose_split. */
+int fd_conv2d_tc_supported(int gathered_channels, int produced_channels);
+int fd_tf32_split(const float* w, float* w_lo, long n, void* stream);
+int fd_weight_transpose_split(const float* w, float* wt, float* wt_lo, int Cout, int taps, int Cin,
+                              void* stream);
+int fd_conv2d_fwd_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                     int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                     int act, void* stream);
+int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, float* dx, int B, int H,
+                       int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream);
 /* dpre = dy * act'(.) computed from the activation output y; dbias[c] += sum_m dpre[m,c] */
 int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long M, int C, int act,
                void* stream);

@@ -157,3 +157,43 @@ def test_adam_matches_torch(cuda):
         ops.adam_step(p, gr.cuda(), m, v, state, 1e-3)
     assert int(state[0]) == 5
     assert rel_err(p.cpu(), ref.detach()) < 1e-6
+
+
+TC_CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad   (real layer shapes of the R18 step, smaller batch)
+    (2, 64, 48, 160, 64, 3, 1, 1),      # layer1
+    (2, 64, 48, 160, 128, 3, 2, 1),     # layer2.0 conv1
+    (2, 64, 48, 160, 128, 1, 2, 0),     # layer2.0 downsample
+    (2, 256, 12, 40, 512, 3, 2, 1),     # layer4.0 conv1
+    (2, 512, 6, 20, 512, 3, 1, 1),      # layer4
+    (1, 96, 98, 322, 32, 3, 1, 0),      # decoder upconv(1,1) on the padded input
+    (1, 32, 98, 322, 16, 3, 1, 0),      # decoder upconv(0,0)
+    (3, 512, 6, 20, 256, 1, 1, 0),      # pose squeeze
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tensor_core_vs_exact_fp32(cuda, case):
+    """tcgen05 3xTF32 path against the exact-fp32 CUDA-core path and an fp64 CPU reference."""
+    from fusiondepth_b200 import ops
+    B, Cin, H, W, Cout, k, s, p = case
+    x = _rand((B, Cin, H, W), 11)
+    w = _rand((Cout, Cin, k, k), 12, (1.0 / (Cin * k * k)) ** 0.5)
+    b = _rand((Cout,), 13, 0.1)
+    ref = F.conv2d(x.double(), w.double(), b.double(), s, p)
+    gy = _rand(tuple(ref.shape), 14)
+    xr = x.double().requires_grad_(True)
+    F.conv2d(xr, w.double(), b.double(), s, p).backward(gy.double())
+    outs = {}
+    for backend in ("tc", "cudacore"):
+        ops.CONV_BACKEND = backend
+        xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+        wc = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
+        yc = ops.conv2d(xc, wc, b.cuda(), s, p, "none")
+        yc.backward(gy.cuda())
+        outs[backend] = (yc.detach().cpu().double(), xc.grad.cpu().double())
+    ops.CONV_BACKEND = "tc"
+    e_tc = rel_err(outs["tc"][0], ref), rel_err(outs["tc"][1], xr.grad)
+    e_cc = rel_err(outs["cudacore"][0], ref), rel_err(outs["cudacore"][1], xr.grad)
+    print("conv %s  fwd err tc %.2e fp32 %.2e | dgrad err tc %.2e fp32 %.2e" % (case, e_tc[0], e_cc[0], e_tc[1], e_cc[1]))
+    assert e_tc[0] < 5e-6 and e_tc[1] < 5e-6, (e_tc, e_cc)
