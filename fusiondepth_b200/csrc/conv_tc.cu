@@ -9,15 +9,15 @@
 //     D[m][n] = sum_k A[m][k] * B[n][k],   m = output pixel, k = (tap, channel)
 // CTA tile 128 (pixels) x BN (channels), K step 32 floats = one 128-byte swizzle row.
 //
-// Roles (288 threads, one CTA per SM):
-//   warps 0-3  loaders: gather the im2col rows of A straight from global memory into a
+// Roles (416 threads, one CTA per SM):
+//   warps 0-7  loaders: gather the im2col rows of A straight from global memory into a
 //              SWIZZLE_128B shared-memory tile with cp.async (zero-fill = padding); one elected
 //              thread fetches the two weight tiles (W, W_lo) with TMA (cp.async.bulk.tensor.2d);
 //              both complete on the stage's `landed` mbarrier;
-//   warps 4-7  splitters: derive the low-order tile A_lo = A - tf32(A) in shared memory, then
+//   warps 8-11 splitters: derive the low-order tile A_lo = A - tf32(A) in shared memory, then
 //              (after the K loop) run the epilogue: tcgen05.ld the accumulators (one pixel row per
 //              thread), bias + activation, vectorised NHWC stores;
-//   warp 8     one elected thread issues tcgen05.mma.kind::tf32 (the tensor core reads the top
+//   warp 12    one elected thread issues tcgen05.mma.kind::tf32 (the tensor core reads the top
 //              19 bits of each fp32 word, so feeding the raw fp32 tile *is* feeding tf32(A)):
 //                  corr  += A_lo*B + A*B_lo          (one TMEM accumulator)
 //                  main_i += A*B                      (round-robin over up to 7 TMEM accumulators)
@@ -35,7 +35,9 @@
 namespace {
 
 constexpr int BM = 128, BK = 32;
-constexpr int NPROD = 128, NTHREADS = 288;
+constexpr int NLOADW = 8, NLOAD = NLOADW * 32;      // loader warps / threads
+constexpr int NSPLIT = 128;                          // splitter (+ epilogue) threads: 4 warps
+constexpr int NTHREADS = NLOAD + NSPLIT + 32;        // + the MMA warp
 constexpr int A_TILE = BM * 128;   // bytes
 
 struct TcArgs {
@@ -186,8 +188,8 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(landed_bar(s), NPROD + 1);   // 128 cp.async completions + 1 expect_tx arrive
-      mbar_init(full_bar(s), NPROD);
+      mbar_init(landed_bar(s), NLOAD + 1);   // cp.async completions + 1 expect_tx arrive
+      mbar_init(full_bar(s), NSPLIT);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
@@ -195,7 +197,7 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wlo) : "memory");
   }
-  if (warp == 8) {
+  if (warp == NLOADW + 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "n"(C::TMEM_COLS)
                  : "memory");
@@ -207,63 +209,73 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp < 4) {
+  if (warp < NLOADW) {
     // ======================= loaders =======================
+    // Everything that depends on the output pixel is hoisted out of the K loop: a base pointer per
+    // row and a bit mask of the valid filter rows / columns (bits 0-7: kh, bits 8-15: kw).  Per
+    // k-block a row costs a mask test, one pointer add and the cp.async.
+    constexpr int ROWS = BM / (NLOAD / 8);          // rows per loader thread
     const int j = tid & 7, rg = tid >> 3;
-    int hb[8], wb[8];
-    long pb[8];
+    const float* rp[ROWS];
+    uint32_t vm[ROWS];
     const int HoWo = a.Ho * a.Wo;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      long m = m0 + rg + 16 * i;
-      if (m < a.M) {
-        int b = (int)(m / HoWo), r = (int)(m % HoWo);
+    for (int i = 0; i < ROWS; ++i) {
+      const int m = (int)m0 + rg + (NLOAD / 8) * i;       // M < 2^31 (checked on the host)
+      rp[i] = a.x;
+      vm[i] = 0;
+      if (m < (int)a.M) {
+        int b = m / HoWo, r = m - b * HoWo;
         int ho = r / a.Wo, wo = r % a.Wo;
-        hb[i] = MODE == 0 ? ho * a.stride - a.pad : ho + a.pad;
-        wb[i] = MODE == 0 ? wo * a.stride - a.pad : wo + a.pad;
-        pb[i] = (long)b * a.Hg * a.Wg;
-      } else {
-        hb[i] = -(1 << 28); wb[i] = 0; pb[i] = 0;
+        int hb, wb, hq, wq;
+        uint32_t mask = 0;
+        if (MODE == 0) {
+          hb = ho * a.stride - a.pad; wb = wo * a.stride - a.pad;
+          hq = hb; wq = wb;
+          for (int t = 0; t < a.KH; ++t) mask |= (uint32_t)(hb + t >= 0 && hb + t < a.Hg) << t;
+          for (int t = 0; t < a.KW; ++t) mask |= (uint32_t)(wb + t >= 0 && wb + t < a.Wg) << (8 + t);
+        } else {
+          hb = ho + a.pad; wb = wo + a.pad;
+          hq = hb / a.stride; wq = wb / a.stride;           // hb, wb >= 0
+          for (int t = 0; t < a.KH; ++t) {
+            int th = hb - t;
+            mask |= (uint32_t)(th >= 0 && th % a.stride == 0 && th / a.stride < a.Hg) << t;
+          }
+          for (int t = 0; t < a.KW; ++t) {
+            int tw = wb - t;
+            mask |= (uint32_t)(tw >= 0 && tw % a.stride == 0 && tw / a.stride < a.Wg) << (8 + t);
+          }
+        }
+        vm[i] = mask;
+        rp[i] = a.x + (((long)b * a.Hg + hq) * a.Wg + wq) * a.Cg + j * 4;
       }
     }
+    const uint32_t soff = (uint32_t)rg * 128u + (uint32_t)((j ^ (rg & 7)) << 4);   // (r & 7) == (rg & 7)
+    int kh = 0, kw = 0, c0 = 0;
     for (int it = 0; it < nk; ++it) {
       const int s = it % C::STAGES;
       if (it >= C::STAGES) mbar_wait(empty_bar(s), ((it / C::STAGES) - 1) & 1);
-      const int k0 = it * BK;
       if (tid == 0) {
         mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
-        tma_load_2d(b_raw(s), &tm_w, k0, n0, landed_bar(s));
-        tma_load_2d(b_lo(s), &tm_wlo, k0, n0, landed_bar(s));
+        tma_load_2d(b_raw(s), &tm_w, it * BK, n0, landed_bar(s));
+        tma_load_2d(b_lo(s), &tm_wlo, it * BK, n0, landed_bar(s));
       }
-      const int tap = k0 / a.Cg, c0 = k0 - tap * a.Cg;
-      const int kh = tap / a.KW, kw = tap - kh * a.KW;
-      const uint32_t ar = a_raw(s);
+      // element offset of this (tap, channel block) relative to the row base pointer
+      const long toff = MODE == 0 ? ((long)kh * a.Wg + kw) * a.Cg + c0
+                                  : -((long)(kh / a.stride) * a.Wg + kw / a.stride) * a.Cg + c0;
+      const uint32_t dst = a_raw(s) + soff;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rg + 16 * i;
-        int h, w;
-        bool ok;
-        if (MODE == 0) {
-          h = hb[i] + kh; w = wb[i] + kw;
-          ok = h >= 0 && h < a.Hg && w >= 0 && w < a.Wg;
-        } else {
-          int th = hb[i] - kh, tw = wb[i] - kw;
-          ok = th >= 0 && tw >= 0;
-          if (a.stride > 1) {
-            ok = ok && (th % a.stride == 0) && (tw % a.stride == 0);
-            th /= a.stride; tw /= a.stride;
-          }
-          h = th; w = tw;
-          ok = ok && h < a.Hg && w < a.Wg;
-        }
-        const float* src = ok ? a.x + ((pb[i] + (long)h * a.Wg + w) * a.Cg + c0 + j * 4) : a.x;
-        cp_async16(ar + r * 128 + ((j ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+      for (int i = 0; i < ROWS; ++i) {
+        const bool ok = ((vm[i] >> kh) & (vm[i] >> (8 + kw)) & 1u) != 0;
+        cp_async16(dst + (uint32_t)i * (NLOAD / 8) * 128u, ok ? rp[i] + toff : a.x, ok ? 16u : 0u);
       }
       cp_async_arrive_noinc(landed_bar(s));
+      c0 += BK;
+      if (c0 == a.Cg) { c0 = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
     }
-  } else if (warp < 8) {
+  } else if (warp < NLOADW + 4) {
     // ======================= splitters, then epilogue =======================
-    const int t = tid - 128;
+    const int t = tid - NLOAD;
     for (int it = 0; it < nk; ++it) {
       const int s = it % C::STAGES;
       mbar_wait(landed_bar(s), (it / C::STAGES) & 1);
@@ -283,7 +295,7 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
       mbar_arrive(full_bar(s));
     }
     // ---- epilogue ----
-    const int ew = warp - 4;
+    const int ew = warp - NLOADW;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const long m = m0 + ew * 32 + lane;
@@ -341,7 +353,7 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NLOADW + 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "n"(C::TMEM_COLS)
@@ -433,6 +445,8 @@ template <int MODE>
 int dispatch_tc(const TcArgs& a, cudaStream_t st) {
   FD_REQUIRE((((uintptr_t)a.w | (uintptr_t)a.wlo | (uintptr_t)a.x) & 15) == 0,
              "conv_tc: operands must be 16-byte aligned");
+  FD_REQUIRE(a.M < (1L << 31) && a.KH <= 8 && a.KW <= 8, "conv_tc: problem too large (M=%ld, %dx%d)", a.M,
+             a.KH, a.KW);
   if (a.N % 128 == 0) return launch_tc<128, MODE>(a, st);
   if (a.N % 64 == 0) return launch_tc<64, MODE>(a, st);
   if (a.N % 32 == 0) return launch_tc<32, MODE>(a, st);

@@ -73,7 +73,7 @@ def parse_roundtrip(calib: Dict[str, np.ndarray] = CALIB) -> Dict[str, np.ndarra
 
 def make_scan(seed: int, n_az: int = 1024,
               ring_deg: Sequence[float] = (1.0, -1.0, -3.0, -4.6),
-              fov_deg: float = 45.0, piled: int = 0) -> np.ndarray:
+              fov_deg: float = 45.0, piled: int = 0, rmin: float = 5.0, rmax: float = 60.0) -> np.ndarray:
     """A sparsified 4-ring velodyne scan [n,4] float32 (x fwd, y left, z up, reflectance),
     following sparsify.py `--H 64 --W 1024 --line_spec 2 7 12 16` (ring centres
     +1,-1,-3,-4.6 deg) and its x/y/z pre-filter (sparsify.py:98-104).  ``piled`` extra
@@ -82,7 +82,7 @@ def make_scan(seed: int, n_az: int = 1024,
     az = np.deg2rad(np.linspace(-fov_deg, fov_deg, n_az, endpoint=False))
     pts = []
     for e in ring_deg:
-        r = rng.uniform(5.0, 60.0, n_az)
+        r = rng.uniform(rmin, rmax, n_az)
         er = np.deg2rad(e + rng.uniform(-0.15, 0.15, n_az))
         pts.append(np.stack([r * np.cos(er) * np.cos(az), r * np.cos(er) * np.sin(az),
                              r * np.sin(er), rng.uniform(0, 1, n_az)], 1))
@@ -140,7 +140,7 @@ def _coherent_frames(B, H, W, g):
 def make_batch(B: int, H: int, W: int, seed: int = 1,
                lidar_fn: Optional[Callable[[np.ndarray], Dict[str, torch.Tensor]]] = None,
                frame_ids=(0, -1, 1), scales=(0, 1, 2, 3), mode: str = "uniform",
-               with_noise: bool = True, lidar_density: float = 0.02) -> Dict:
+               with_noise: bool = True, lidar_density: float = 0.02, scan_range=(5.0, 60.0)) -> Dict:
     """One micro-batch keyed like the reference loader's output, all CPU fp32.
 
     ``lidar_fn(points[n,4] float32) -> {"4beam": [1,H,W], "2channel": [2,H,W]}``; when it
@@ -167,7 +167,7 @@ def make_batch(B: int, H: int, W: int, seed: int = 1,
     for b in range(B):
         for f in frame_ids:
             if lidar_fn is not None:
-                m = lidar_fn(make_scan(seed * 1000 + b * 7 + (f + 1)))
+                m = lidar_fn(make_scan(seed * 1000 + b * 7 + (f + 1), rmin=scan_range[0], rmax=scan_range[1]))
                 fb, tc = m["4beam"], m["2channel"]
             else:
                 mask = (torch.rand(1, H, W, generator=g) < lidar_density).float()

@@ -98,13 +98,63 @@ def draw_noise(B, H, W, device):
     return {s: torch.randn(B, 2, H, W).to(device) for s in range(4)}
 
 
+class TrunkStreams:
+    """Side streams for the six independent ResNet trunks of one micro-batch.  The trunks share
+    no data until the decoder / pose heads, so they are issued on separate CUDA streams (forked
+    from and joined back to the current stream with events); inside a captured CUDA graph this
+    becomes six parallel branches, which keeps all 148 SMs busy through the small layer3/layer4
+    GEMMs.  Autograd replays each branch's backward on the stream its forward ran on."""
+
+    def __init__(self, device, n: int = 5):
+        self.side = [torch.cuda.Stream(device=device) for _ in range(n)]
+
+    def fork(self):
+        cur = torch.cuda.current_stream()
+        for s in self.side:
+            s.wait_stream(cur)
+
+    def join(self, idx):
+        cur = torch.cuda.current_stream()
+        for i in idx:
+            cur.wait_stream(self.side[i])
+
+
 def process_batch(models, inputs, noise=None, opts: Optional[Dict] = None, materialize=False,
-                  frame_ids=(0, -1, 1)):
+                  frame_ids=(0, -1, 1), streams: Optional[TrunkStreams] = None):
     """Trainer.process_batch (trainer.py:268-319), default flags."""
-    feats = models["encoder"](inputs[("color_aug", 0, 0)])
-    beam = models["beam_encoder"](inputs["2channel"])
-    outputs = dict(models["depth"](feats, beam_features=beam))
-    outputs.update(predict_poses(models, inputs, frame_ids))
+    if streams is None:
+        feats = models["encoder"](inputs[("color_aug", 0, 0)])
+        beam = models["beam_encoder"](inputs["2channel"])
+        outputs = dict(models["depth"](feats, beam_features=beam))
+        outputs.update(predict_poses(models, inputs, frame_ids))
+    else:
+        # same call sequence, trunks on parallel streams
+        streams.fork()
+        side = streams.side
+        with torch.cuda.stream(side[0]):
+            beam = models["beam_encoder"](inputs["2channel"])
+        pose_feats, pose_beam = {}, {}
+        for n, f_i in enumerate(frame_ids[1:]):
+            pair = (f_i, 0) if f_i < 0 else (0, f_i)
+            with torch.cuda.stream(side[1 + 2 * n]):
+                img = torch.cat([inputs[("color_aug", i, 0)] for i in pair], 1)
+                pose_feats[f_i] = [models["pose_encoder"](img)]
+            with torch.cuda.stream(side[2 + 2 * n]):
+                two = torch.cat([inputs[("2channel", i, 0)] for i in pair], 1)
+                pose_beam[f_i] = [models["beam_encoder_pose"](two)]
+        feats = models["encoder"](inputs[("color_aug", 0, 0)])
+        streams.join([0])
+        outputs = dict(models["depth"](feats, beam_features=beam))
+        for n, f_i in enumerate(frame_ids[1:]):
+            sp, sb = side[1 + 2 * n], side[2 + 2 * n]
+            sp.wait_stream(sb)
+            with torch.cuda.stream(sp):
+                axisangle, translation = models["pose"](pose_feats[f_i], beam_inputs=pose_beam[f_i])
+                outputs[("axisangle", 0, f_i)] = axisangle
+                outputs[("translation", 0, f_i)] = translation
+                outputs[("cam_T_cam", 0, f_i)] = transformation_from_parameters(
+                    axisangle[:, 0], translation[:, 0], invert=(f_i < 0))
+        streams.join([1, 2, 3, 4])
     if noise is None:
         B, _, H, W = inputs[("color", 0, 0)].shape
         noise = draw_noise(B, H, W, inputs[("color", 0, 0)].device)
@@ -182,7 +232,7 @@ class TrainStep:
     gradient buffer is averaged across ranks with one NCCL all-reduce before Adam."""
 
     def __init__(self, models, lr: float = 1e-4, accumulate: int = 1, opts: Optional[Dict] = None,
-                 process_group=None):
+                 process_group=None, parallel_trunks: bool = True):
         self.models = models
         self.accumulate = accumulate
         self.lr = float(lr)
@@ -196,6 +246,8 @@ class TrainStep:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        self.streams = TrunkStreams(dev) if parallel_trunks else None
+        self.stream = torch.cuda.Stream(device=dev)      # warm-up and capture share one stream
         self.graph = None
         self.static_inputs = None
         self.static_noise = None
@@ -208,7 +260,7 @@ class TrainStep:
         self.flat.zero_grad()
         total = None
         for inputs, noise in zip(batches, noises):
-            _, losses = process_batch(self.models, inputs, noise, self.opts)
+            _, losses = process_batch(self.models, inputs, noise, self.opts, streams=self.streams)
             loss = losses["loss"] / self.accumulate
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
@@ -230,7 +282,7 @@ class TrainStep:
         self.static_noise = [{k: v.clone() for k, v in n.items()} for n in noises]
         keep = (self.flat.data.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
                 self.adam_state.clone(), self._bn_state())
-        s = torch.cuda.Stream()
+        s = self.stream
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -238,7 +290,7 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=s):
             self.loss_out = self._run(self.static_inputs, self.static_noise)
         # undo the warm-up / capture side effects on the training state
         self.flat.data.copy_(keep[0]); self.exp_avg.copy_(keep[1]); self.exp_avg_sq.copy_(keep[2])

@@ -25,16 +25,26 @@ SHAPES = [  # B, Cin, H, W, Cout, k, s, p, name
 
 
 def timeit(fn, n=10):
-    for _ in range(3):
+    """kernel-only time: the calls are captured in a CUDA graph so Python/launch overhead vanishes"""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
         fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        fn()
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n
+    return e0.elapsed_time(e1) / (3 * n)
 
 
 for B, Cin, H, W, Cout, k, s, p, name in SHAPES:
@@ -48,7 +58,9 @@ for B, Cin, H, W, Cout, k, s, p, name in SHAPES:
         ops.CONV_BACKEND = backend
         with torch.no_grad():
             tf = timeit(lambda: ops.conv2d(x, w, None, s, p, "none"))
-        y = ops.conv2d(x, w, None, s, p, "none")
-        tb = timeit(lambda: torch.autograd.grad(y, (x, w), gy, retain_graph=True))
+        def fb():
+            y = ops.conv2d(x, w, None, s, p, "none")
+            torch.autograd.grad(y, (x, w), gy)
+        tb = timeit(fb) - tf
         row += "| %s fwd %.3f ms (%.1f TF) bwd %.3f ms " % (backend, tf, flop / tf / 1e9, tb)
     print(row)
