@@ -66,6 +66,7 @@ _SIGNATURES = {
     "fd_weight_transpose_split": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "fd_conv2d_fwd_tc": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_dgrad_tc": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_conv2d_wgrad_tc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_act_bwd": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P]),
     "fd_bn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P, _L, _I, _P]),
     "fd_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _P]),

@@ -28,6 +28,7 @@
 // Stage hand-off is mbarrier based (landed: cp.async + TMA tx; full: 128 splitter arrivals;
 // empty / accumulator-ready: tcgen05.commit).  W_lo = W - tf32(W) comes from fd_tf32_split.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/fusiondepth_b200.h"
@@ -361,6 +362,233 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
   }
 }
 
+
+// ================================================================================================
+// Weight gradient on the tensor cores:  dW[n][k] += sum_p dY[p][n] * X_im2col[p][k]
+//
+// GEMM view: D'[k][n] with M' = 128 consecutive k (four 32-channel groups of one or more filter
+// taps), N' = BN output channels, reduction over the pixels p.  Both operands are "MN-major" for
+// the tensor core (the reduction index p is the strided one): their shared-memory image is the
+// [pixel rows x 128 B] block per 32 channels, in the SWIZZLE_128B_BASE32B pattern that MN-major tf32
+// operands require.
+//   A' = gathered input pixels (cp.async, zero-fill outside the image) -> 4 blocks of [32 px x 128 B]
+//   B' = dY rows (TMA 2-D boxes, rows past M zero-filled by the TMA unit) -> BN/32 blocks
+// 3xTF32: both low-order tiles are produced by the splitter warps.  The pixel range is split over
+// blockIdx.z; partial results are added to dW with coalesced fp32 reductions (red.global.add).
+// ================================================================================================
+constexpr int BP = 32;                       // pixels (reduction elements) per stage
+constexpr int BLK = BP * 128;                // bytes of one [32 px x 32 ch] block
+
+struct WgTcArgs {
+  const float* x;   // [B,H,W,Cin]
+  float* dw;        // [N][K]
+  int B, H, W, Cin, Ho, Wo, N, KH, KW, stride, pad;
+  int M, K;
+  int p_per_split;  // pixels per blockIdx.z (multiple of BP)
+  int dbg;
+};
+
+// MN-major tf32 operands must use the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms: within a
+// 128-byte row the 32-byte chunk index is XORed with row & 3; 4-row groups of 512 B).  Descriptor:
+// 32-float column blocks `lbo` bytes apart, 4-row groups 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+template <int BN>
+struct WgCfg {
+  static constexpr int NB = BN / 32;                       // dY column blocks
+  static constexpr int A_BYTES = 4 * BLK, B_BYTES = NB * BLK;
+  static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 512 : 256);
+  static constexpr int NMAIN = TMEM_COLS / BN - 1 > 7 ? 7 : TMEM_COLS / BN - 1;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
+  using C = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + C::STAGES * C::STAGE;
+  auto landed_bar = [&](int s) { return bars + 8u * s; };
+  auto full_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  const uint32_t acc_bar = bars + 8u * (3 * C::STAGES);
+  const uint32_t tmem_slot = acc_bar + 8u;
+  auto a_raw = [&](int s) { return base + s * C::STAGE; };
+  auto a_lo = [&](int s) { return base + s * C::STAGE + C::A_BYTES; };
+  auto b_raw = [&](int s) { return base + s * C::STAGE + 2 * C::A_BYTES; };
+  auto b_lo = [&](int s) { return base + s * C::STAGE + 2 * C::A_BYTES + C::B_BYTES; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int pbeg = blockIdx.z * a.p_per_split;
+  const int pend = min(a.M, pbeg + a.p_per_split);
+  const int nst = (pend - pbeg + BP - 1) / BP;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed_bar(s), NLOAD + 1);
+      mbar_init(full_bar(s), NSPLIT);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dy) : "memory");
+  }
+  if (warp == NLOADW + 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < NLOADW) {
+    // ======================= loaders: thread = (pixel row rg, 16-byte chunk j) =======================
+    const int j = tid & 7, rg = tid >> 3;            // 32 rows x 8 chunks = 256 threads
+    int kh[4], kw[4], cc[4];
+    bool kok[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int k = k0 + 32 * c;
+      kok[c] = k < a.K;
+      int tap = kok[c] ? k / a.Cin : 0;
+      cc[c] = k - tap * a.Cin;
+      kh[c] = tap / a.KW; kw[c] = tap - kh[c] * a.KW;
+    }
+    const int HoWo = a.Ho * a.Wo;
+    const uint32_t soff = (uint32_t)rg * 128u + (uint32_t)((((j >> 1) ^ (rg & 3)) << 5) | ((j & 1) << 4));
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % C::STAGES;
+      if (it >= C::STAGES) mbar_wait(empty_bar(s), ((it / C::STAGES) - 1) & 1);
+      const int p0 = pbeg + it * BP;
+      if (tid == 0) {
+        mbar_expect_tx(landed_bar(s), C::B_BYTES);
+#pragma unroll
+        for (int nb = 0; nb < C::NB; ++nb) tma_load_2d(b_raw(s) + nb * BLK, &tm_dy, n0 + 32 * nb, p0, landed_bar(s));
+      }
+      const int p = p0 + rg;
+      const bool pok = p < pend;
+      int b = 0, ho = 0, wo = 0;
+      if (pok) { b = p / HoWo; int r = p - b * HoWo; ho = r / a.Wo; wo = r - ho * a.Wo; }
+      const int hb = ho * a.stride - a.pad, wb = wo * a.stride - a.pad;
+      const uint32_t dst = a_raw(s) + soff;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int h = hb + kh[c], w = wb + kw[c];
+        const bool ok = pok && kok[c] && h >= 0 && h < a.H && w >= 0 && w < a.W;
+        const float* src = ok ? a.x + (((long)b * a.H + h) * a.W + w) * a.Cin + cc[c] + j * 4 : a.x;
+        cp_async16(dst + c * BLK, src, ok ? 16u : 0u);
+      }
+      cp_async_arrive_noinc(landed_bar(s));
+    }
+  } else if (warp < NLOADW + 4) {
+    // ======================= splitters, then epilogue =======================
+    const int t = tid - NLOAD;
+    constexpr int NV = (C::A_BYTES + C::B_BYTES) / 16 / NSPLIT;     // float4 per thread per stage
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % C::STAGES;
+      mbar_wait(landed_bar(s), (it / C::STAGES) & 1);
+      // (dY rows past `pend` meet all-zero A' rows, rows past M are zero-filled by the TMA unit)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t idx = (uint32_t)(t + NSPLIT * i);
+        const bool isA = idx < C::A_BYTES / 16;
+        const uint32_t so = (isA ? idx : idx - C::A_BYTES / 16) * 16u;
+        const uint32_t src = (isA ? a_raw(s) : b_raw(s)) + so, dst = (isA ? a_lo(s) : b_lo(s)) + so;
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(src));
+        if ((a.dbg == 2 && isA) || (a.dbg == 3 && !isA) || a.dbg == 4) {
+          v = make_float4(1.f, 1.f, 1.f, 1.f);
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(src), "f"(1.f), "f"(1.f), "f"(1.f), "f"(1.f) : "memory");
+        }
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(lo_part(v.x)),
+                     "f"(lo_part(v.y)), "f"(lo_part(v.z)), "f"(lo_part(v.w))
+                     : "memory");
+      }
+      fence_async_proxy();
+      mbar_arrive(full_bar(s));
+    }
+    const int ew = warp - NLOADW;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int k = k0 + ew * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
+    const int nmain = nst < C::NMAIN ? nst : C::NMAIN;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float acc[16], tmp[16];
+      tmem_ld16(trow + (uint32_t)(BN + c), acc);
+      for (int q = 1; q < nmain; ++q) {
+        tmem_ld16(trow + (uint32_t)((1 + q) * BN + c), tmp);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] += tmp[e];
+      }
+      tmem_ld16(trow + (uint32_t)c, tmp);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] += tmp[e];
+      if (a.dbg == 1) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 1.0f;
+      }
+      if (k < a.K && nst > 0) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (n0 + c + e < a.N) atomicAdd(a.dw + (long)(n0 + c + e) * a.K + k, acc[e]);
+      }
+    }
+  } else {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(full_bar(s), (it / C::STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = make_desc_mn(a_raw(s), BLK), dal = make_desc_mn(a_lo(s), BLK);
+        const uint64_t db = make_desc_mn(b_raw(s), BLK), dbl = make_desc_mn(b_lo(s), BLK);
+        const uint32_t d_corr = tmem_base;
+        const uint32_t d_main = tmem_base + (uint32_t)((1 + it % C::NMAIN) * BN);
+#pragma unroll
+        for (int k = 0; k < BP / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 1024 >> 4);        // next 8-pixel row group
+          umma_tf32(d_corr, dal + adv, db + adv, idesc, (it | k) != 0);
+          umma_tf32(d_corr, da + adv, dbl + adv, idesc, 1);
+          umma_tf32(d_main, da + adv, db + adv, idesc, (it >= C::NMAIN) || (k != 0));
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(acc_bar);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NLOADW + 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 __global__ void tf32_split_kernel(const float* __restrict__ w, float* __restrict__ lo, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float v = w[i];
@@ -402,7 +630,8 @@ EncodeTiledFn encode_tiled() {
 }
 
 // 2-D fp32 tensor [rows][cols] (cols contiguous), box = 32 cols x box_rows, SWIZZLE_128B
-int make_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, int box_rows) {
+int make_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, int box_rows,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = encode_tiled();
   FD_REQUIRE(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -410,7 +639,7 @@ int make_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, int bo
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FD_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld", (int)r,
              rows, cols);
@@ -451,6 +680,37 @@ int dispatch_tc(const TcArgs& a, cudaStream_t st) {
   if (a.N % 64 == 0) return launch_tc<64, MODE>(a, st);
   if (a.N % 32 == 0) return launch_tc<32, MODE>(a, st);
   return launch_tc<16, MODE>(a, st);
+}
+
+
+template <int BN>
+int launch_wgrad_tc(const WgTcArgs& a0, const float* dy, cudaStream_t st) {
+  using C = WgCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) {
+      fd::set_error("conv_wgrad_tc: cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  WgTcArgs a = a0;
+  CUtensorMap tdy;
+  int rc = make_map_2d(&tdy, dy, a.M, a.N, BP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const int tiles = fd::cdiv(a.K, 128) * (a.N / BN);
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  const int max_splits = fd::cdiv(a.M, 4 * BP);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.p_per_split = fd::cdiv(fd::cdiv(a.M, splits), BP) * BP;
+  splits = fd::cdiv(a.M, a.p_per_split);
+  dim3 grid(fd::cdiv(a.K, 128), a.N / BN, splits);
+  conv_wgrad_tc_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(a, tdy);
+  FD_CHECK_LAUNCH();
+  return 0;
 }
 
 }  // namespace
@@ -505,6 +765,29 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
   a.M = (long)B * H * W;
   a.K = KH * KW * Cout;
   return dispatch_tc<1>(a, (cudaStream_t)stream);
+}
+
+int fd_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin,
+                       int Cout, int KH, int KW, int stride, int pad, void* stream) {
+  FD_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0,
+             "fd_conv2d_wgrad_tc: needs Cin %% 32 == 0 and Cout %% 32 == 0 (got %d, %d)", Cin, Cout);
+  WgTcArgs a;
+  a.x = x; a.dw = dw;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+  a.Ho = (H + 2 * pad - KH) / stride + 1;
+  a.Wo = (W + 2 * pad - KW) / stride + 1;
+  a.N = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
+  long M = (long)B * a.Ho * a.Wo;
+  FD_REQUIRE(M < (1L << 31), "fd_conv2d_wgrad_tc: too many pixels");
+  a.M = (int)M;
+  a.K = KH * KW * Cin;
+  a.p_per_split = 0;
+  a.dbg = getenv("FD_WGRAD_DEBUG") ? atoi(getenv("FD_WGRAD_DEBUG")) : 0;
+  FD_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "conv_wgrad_tc: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cout % 128 == 0) return launch_wgrad_tc<128>(a, dy, st);
+  if (Cout % 64 == 0) return launch_wgrad_tc<64>(a, dy, st);
+  return launch_wgrad_tc<32>(a, dy, st);
 }
 
 }  // extern "C"

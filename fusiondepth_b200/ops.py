@@ -164,8 +164,12 @@ class Conv2dFn(torch.autograd.Function):
             dw = torch.empty((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32,
                              memory_format=CL).zero_()
             with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
-                _lib.check(lib.fd_conv2d_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
-                                               stride, pad, st), "fd_conv2d_wgrad")
+                if CONV_BACKEND == "tc" and Cin % 32 == 0 and Cout % 32 == 0:
+                    _lib.check(lib.fd_conv2d_wgrad_tc(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
+                                                      stride, pad, st), "fd_conv2d_wgrad_tc")
+                else:
+                    _lib.check(lib.fd_conv2d_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
+                                                   stride, pad, st), "fd_conv2d_wgrad")
         return dx, dw, dbias, None, None, None
 
 

@@ -127,6 +127,10 @@ int fd_conv2d_fwd_tc(const float* x, const float* w, const float* w_lo, const fl
                      int act, void* stream);
 int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, float* dx, int B, int H,
                        int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream);
+/* dw [Cout,KH,KW,Cin] += ... on the tensor cores (Cin and Cout multiples of 32); dw must be
+ * zero-initialised or hold an accumulator. */
+int fd_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin,
+                       int Cout, int KH, int KW, int stride, int pad, void* stream);
 /* dpre = dy * act'(.) computed from the activation output y; dbias[c] += sum_m dpre[m,c] */
 int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long M, int C, int act,
                void* stream);

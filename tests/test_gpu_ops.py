@@ -183,7 +183,8 @@ def test_conv_tensor_core_vs_exact_fp32(cuda, case):
     ref = F.conv2d(x.double(), w.double(), b.double(), s, p)
     gy = _rand(tuple(ref.shape), 14)
     xr = x.double().requires_grad_(True)
-    F.conv2d(xr, w.double(), b.double(), s, p).backward(gy.double())
+    wr = w.double().requires_grad_(True)
+    F.conv2d(xr, wr, b.double(), s, p).backward(gy.double())
     outs = {}
     for backend in ("tc", "cudacore"):
         ops.CONV_BACKEND = backend
@@ -191,9 +192,10 @@ def test_conv_tensor_core_vs_exact_fp32(cuda, case):
         wc = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
         yc = ops.conv2d(xc, wc, b.cuda(), s, p, "none")
         yc.backward(gy.cuda())
-        outs[backend] = (yc.detach().cpu().double(), xc.grad.cpu().double())
+        outs[backend] = (yc.detach().cpu().double(), xc.grad.cpu().double(), wc.grad.cpu().double())
     ops.CONV_BACKEND = "tc"
-    e_tc = rel_err(outs["tc"][0], ref), rel_err(outs["tc"][1], xr.grad)
-    e_cc = rel_err(outs["cudacore"][0], ref), rel_err(outs["cudacore"][1], xr.grad)
-    print("conv %s  fwd err tc %.2e fp32 %.2e | dgrad err tc %.2e fp32 %.2e" % (case, e_tc[0], e_cc[0], e_tc[1], e_cc[1]))
-    assert e_tc[0] < 5e-6 and e_tc[1] < 5e-6, (e_tc, e_cc)
+    e_tc = [rel_err(outs["tc"][i], r) for i, r in enumerate((ref, xr.grad, wr.grad))]
+    e_cc = [rel_err(outs["cudacore"][i], r) for i, r in enumerate((ref, xr.grad, wr.grad))]
+    print("conv %s  fwd err tc %.2e fp32 %.2e | dgrad tc %.2e fp32 %.2e | wgrad tc %.2e fp32 %.2e"
+          % (case, e_tc[0], e_cc[0], e_tc[1], e_cc[1], e_tc[2], e_cc[2]))
+    assert e_tc[0] < 5e-6 and e_tc[1] < 5e-6 and e_tc[2] < 2e-5, (e_tc, e_cc)
