@@ -181,6 +181,12 @@ def cpu_baseline_leg():
 
 
 # ------------------------------------------------------------------------------------------------
+def _phase(msg):
+    if os.environ.get("FD_BENCH_VERBOSE"):
+        sys.stderr.write("[bench rank %s] %s\n" % (os.environ.get("RANK", "0"), msg))
+        sys.stderr.flush()
+
+
 def run_ours(args):
     from fusiondepth_b200 import _lib, ops, synth, training
     _lib.load()                                   # no CUDA extension => fail loudly
@@ -193,6 +199,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=dev)
 
+    _phase("process group up")
     torch.manual_seed(0)                          # same initial weights on every rank
     models = training.build_models(NUM_LAYERS, dev)
     step = training.TrainStep(models, lr=1e-4 * (MICRO_B * ACCUM) / 8, accumulate=ACCUM)
@@ -203,6 +210,8 @@ def run_ours(args):
         sum(v.numel() * v.element_size() for n in pinned_noise for v in n.values())
     batches = [synth.to_device(b, dev) for b in cpu_batches]
     noises = [{s: t.to(dev) for s, t in n.items()} for n in cpu_noises]
+
+    _phase("inputs ready")
 
     def barrier():
         if world > 1:
@@ -241,13 +250,16 @@ def run_ours(args):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t) / k, out
 
+    _phase("captured / first step done, launches/step=%d" % launches_per_step)
     first_loss = float(run())
+    _phase("first replay done")
     for _ in range(max(args.warmup, 3) - 1):
         run()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms, loss = timed(run, args.steps)
+    _phase("timed region done: %.2f ms/step" % ms)
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: pinned host inputs -> H2D -> step -> D2H loss, every step
@@ -267,19 +279,25 @@ def run_ours(args):
 
     e2e_step()
     ms_e2e, _ = timed(e2e_step, args.steps)
+    _phase("e2e done")
+
+    # per-kernel-family device times from one instrumented eager step on rank 0 alone, with the
+    # gradient all-reduce switched off (no collective may run on a single rank)
+    fam = {}
+    if rank == 0:
+        ops.PROFILE = {}
+        step.world = 1
+        step.step(batches, noises)
+        torch.cuda.synchronize()
+        for name, evs in ops.PROFILE.items():
+            fam[name] = (sum(s.elapsed_time(e) for s, e, _ in evs), sum(w for _, _, w in evs), len(evs))
+        ops.PROFILE = None
+    _phase("instrumented step done")
 
     result = None
     if rank == 0:
         imgs = MICRO_B * ACCUM * world
         pk = peaks()
-        # per-kernel-family device times from one instrumented eager step
-        ops.PROFILE = {}
-        step.step(batches, noises)
-        torch.cuda.synchronize()
-        fam = {}
-        for name, evs in ops.PROFILE.items():
-            fam[name] = (sum(s.elapsed_time(e) for s, e, _ in evs), sum(w for _, _, w in evs), len(evs))
-        ops.PROFILE = None
         conv_ms, conv_flop, conv_n = fam.get("conv", (0.0, 0.0, 0))
         pl_ms = fam["photoloss_fwd"][0] + fam["photoloss_bwd"][0]
         pl_bytes = fam["photoloss_fwd"][1] + fam["photoloss_bwd"][1]
@@ -311,11 +329,16 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline_leg()
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
     if result is not None:
         print(json.dumps(result))
+        sys.stdout.flush()
+    if world > 1:
+        # A communicator that is referenced by a captured CUDA graph does not tear down cleanly
+        # (destroy_process_group blocks); the line is out, so leave without the NCCL teardown.
+        torch.cuda.synchronize()
+        _phase("exit")
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -226,6 +226,16 @@ class FlatParams:
         self.grad.zero_()
 
 
+def reduce_gradients(flat: "FlatParams", world: int, group=None):
+    """The data-parallel exchange step: ONE sum all-reduce of the flat gradient buffer (NCCL over
+    NVLink on GPUs; the 1/world average is folded into the Adam kernel's grad_scale).  Samples are
+    independent through the whole step and BatchNorm statistics stay per rank, as in the
+    single-process reference, so this is the only collective on the path."""
+    if world > 1:
+        torch.distributed.all_reduce(flat.grad, op=torch.distributed.ReduceOp.SUM, group=group)
+    return flat.grad
+
+
 class TrainStep:
     """One optimiser step of trainer.py:237-248: ``accumulate`` micro-batches, each
     process_batch -> (loss/accumulate).backward(), then Adam.  With world_size > 1 the flat
@@ -264,8 +274,7 @@ class TrainStep:
             loss = losses["loss"] / self.accumulate
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat.grad, group=self.pg)
+        reduce_gradients(self.flat, self.world, self.pg)
         ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.adam_state,
                       self.lr, grad_scale=1.0 / self.world)
         return total
