@@ -204,11 +204,33 @@ def gen_loss_chain(ns, B=2, H=96, W=160):
     print("loss_chain", {k: float(v) for k, v in losses.items()})
 
 
+def gen_state_dict_keys(ns):
+    """key -> shape of every network variant the drivers build, from the REFERENCE modules."""
+    import json
+    N = ns.networks
+    ch = np.array([64, 64, 128, 256, 512])
+    built = {
+        "enc18": N.ResnetEncoder(18, False), "enc50": N.ResnetEncoder(50, False),
+        "beam18": N.ResnetEncoder(18, False, beam_encoder=True),
+        "pose18": N.ResnetEncoder(18, False, num_input_images=2),
+        "beampose18": N.ResnetEncoder(18, False, num_input_images=2, beam_encoder=True),
+        "refineenc18": N.ResnetEncoder(18, False, refine_encoder=True),
+        "depth": N.DepthDecoder(ch, [0, 1, 2, 3]),
+        "refine2d": N.DepthDecoder(ch, [0, 1, 2, 3], road=True, catxy=True, deep=True),
+        "cat2end": N.DepthDecoder(ch, [0, 1, 2, 3], cat2end=True),
+        "pose": N.PoseDecoder(ch, 1, 2), "posecnn": N.PoseCNN(2),
+    }
+    out = {k: [[kk, list(v.shape)] for kk, v in m.state_dict().items()] for k, m in built.items()}
+    json.dump(out, open(os.path.join(GOLDEN, "state_dict_keys.json"), "w"))
+
+
 if __name__ == "__main__":
     assert RH.available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN, exist_ok=True)
     ns = RH.load()
-    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss"]
+    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss", "keys"]
+    if "keys" in which:
+        gen_state_dict_keys(ns)
     if "lidar" in which:
         gen_lidar(ns)
     if "step" in which:
@@ -217,3 +239,4 @@ if __name__ == "__main__":
         gen_forward_variants(ns)
     if "loss" in which:
         gen_loss_chain(ns)
+

@@ -1,0 +1,89 @@
+"""The reference-facing module surface (names, signatures, state-dict keys) and the unfused
+geometry layers vs the oracle -- CPU only."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from tests._util import GOLDEN, ROOT, rel_err
+from oracle import step_oracle as SO
+
+
+def test_layers_exports_what_the_drivers_use():
+    from fusiondepth_b200 import layers
+    for name in ("disp_to_depth", "transformation_from_parameters", "rot_from_axisangle",
+                 "get_translation_matrix", "ConvBlock", "Conv3x3", "BackprojectDepth", "Cat_xy",
+                 "Project3D", "upsample", "get_smooth_loss", "SSIM", "compute_depth_errors",
+                 "F", "nn", "np", "torch"):
+        assert hasattr(layers, name), name
+
+
+def test_dropin_shims_resolve():
+    sys.path.insert(0, os.path.join(ROOT, "fusiondepth_b200", "dropin"))
+    try:
+        for m in ("layers", "networks"):
+            sys.modules.pop(m, None)
+        import layers as L
+        import networks as N
+        assert L.F is torch.nn.functional and L.nn is torch.nn
+        assert N.ResnetEncoder.__module__.startswith("fusiondepth_b200")
+        assert {"ResnetEncoder", "DepthDecoder", "PoseDecoder", "PoseCNN"} <= set(dir(N))
+    finally:
+        sys.path.pop(0)
+        for m in ("layers", "networks"):
+            sys.modules.pop(m, None)
+
+
+def test_state_dict_contract():
+    """key -> shape of every network variant the drivers build, against the keys recorded from the
+    reference modules (tests/golden/state_dict_keys.json, written by make_golden.py)."""
+    from fusiondepth_b200 import networks as N
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    ch = np.array([64, 64, 128, 256, 512])
+    built = {
+        "enc18": N.ResnetEncoder(18, False), "enc50": N.ResnetEncoder(50, False),
+        "beam18": N.ResnetEncoder(18, False, beam_encoder=True),
+        "pose18": N.ResnetEncoder(18, False, num_input_images=2),
+        "beampose18": N.ResnetEncoder(18, False, num_input_images=2, beam_encoder=True),
+        "refineenc18": N.ResnetEncoder(18, False, refine_encoder=True),
+        "depth": N.DepthDecoder(ch, [0, 1, 2, 3]),
+        "refine2d": N.DepthDecoder(ch, [0, 1, 2, 3], road=True, catxy=True, deep=True),
+        "cat2end": N.DepthDecoder(ch, [0, 1, 2, 3], cat2end=True),
+        "pose": N.PoseDecoder(ch, 1, 2), "posecnn": N.PoseCNN(2),
+    }
+    for name, m in built.items():
+        got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        assert got == want[name], name
+    with __import__("pytest").raises(ValueError):
+        N.ResnetEncoder(19, False)
+
+
+def test_geometry_layers_match_oracle():
+    from fusiondepth_b200 import layers as L
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 2, 16, 24
+    depth = 0.5 + torch.rand(B, 1, H, W, generator=g) * 10
+    K = torch.tensor([[0.58 * W, 0, 0.5 * W, 0], [0, 1.92 * H, 0.5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1.]]).repeat(B, 1, 1)
+    invK = torch.linalg.pinv(K)
+    aa, tt = 0.02 * torch.randn(B, 1, 3, generator=g), 0.1 * torch.randn(B, 1, 3, generator=g)
+    for inv in (False, True):
+        assert rel_err(L.transformation_from_parameters(aa, tt, inv), SO.pose_matrix(aa, tt, inv)) < 1e-6
+    T = L.transformation_from_parameters(aa, tt, False)
+    pts = L.BackprojectDepth(B, H, W)(depth, invK)
+    assert rel_err(pts, SO.backproject(depth, invK)) < 1e-6
+    assert rel_err(L.Project3D(B, H, W)(pts, K, T), SO.project(pts, K, T, H, W)) < 1e-6
+    assert rel_err(L.Cat_xy(B, H, W)(depth, invK), SO.cat_xy(depth, invK)) < 1e-6
+    x, y = torch.rand(B, 3, H, W, generator=g), torch.rand(B, 3, H, W, generator=g)
+    assert rel_err(L.SSIM()(x, y), SO.ssim(x, y)) < 1e-6
+    disp = torch.rand(B, 1, H, W, generator=g)
+    assert rel_err(L.get_smooth_loss(disp, x), SO.smooth_loss(disp, x)) < 1e-6
+    sd, d = L.disp_to_depth(disp, 0.1, 100.0)
+    osd, od = SO.disp_to_depth(disp, 0.1, 100.0)
+    assert torch.equal(sd, osd) and torch.equal(d, od)
+    errs = L.compute_depth_errors(depth, depth * 1.1)
+    assert abs(float(errs[0]) - 0.1) < 1e-5 and float(errs[4]) == 1.0
+    # batch-size mismatch surfaces as a RuntimeError, like the reference
+    with __import__("pytest").raises(RuntimeError):
+        L.BackprojectDepth(B + 1, H, W)(depth, invK)
