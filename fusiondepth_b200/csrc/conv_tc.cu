@@ -676,9 +676,12 @@ int dispatch_tc(const TcArgs& a, cudaStream_t st) {
              "conv_tc: operands must be 16-byte aligned");
   FD_REQUIRE(a.M < (1L << 31) && a.KH <= 8 && a.KW <= 8, "conv_tc: problem too large (M=%ld, %dx%d)", a.M,
              a.KH, a.KW);
-  if (a.N % 128 == 0) return launch_tc<128, MODE>(a, st);
-  if (a.N % 64 == 0) return launch_tc<64, MODE>(a, st);
-  if (a.N % 32 == 0) return launch_tc<32, MODE>(a, st);
+  // Tile width: the widest BN dividing N.  (Narrower tiles for the few-pixel layers were measured
+  // slower once the six trunks run concurrently: every extra N-tile repeats the A gather + split.)
+  const int bn = a.N % 128 == 0 ? 128 : (a.N % 64 == 0 ? 64 : (a.N % 32 == 0 ? 32 : 16));
+  if (bn == 128) return launch_tc<128, MODE>(a, st);
+  if (bn == 64) return launch_tc<64, MODE>(a, st);
+  if (bn == 32) return launch_tc<32, MODE>(a, st);
   return launch_tc<16, MODE>(a, st);
 }
 

@@ -60,36 +60,85 @@ __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restr
 }
 
 // ---- BatchNorm -------------------------------------------------------------------------------
-// pass 1: per-channel sum / sum of squares in fp64
+// Every thread owns VEC consecutive channels (float4 when C % 4 == 0) and strides over pixels with
+// four independent loads in flight; block = (channel groups, pixel lanes), 256 threads.
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using T = float4; };
+template <> struct VecT<1> { using T = float; };
+template <int VEC>
+__device__ __forceinline__ void ldv(const float* p, float (&v)[VEC]) {
+  if (VEC == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[VEC - 1] = t.w; }
+  else v[0] = p[0];
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const float (&v)[VEC]) {
+  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[VEC - 1]);
+  else p[0] = v[0];
+}
+
+struct BnGeom { int groups, gx, gy; dim3 grid, block; };
+inline BnGeom bn_geom(long M, int C, int vec) {
+  BnGeom g;
+  g.groups = C / vec;
+  g.gx = g.groups < 32 ? g.groups : 32;          // channel groups per block row
+  g.gy = 256 / g.gx;                              // pixel lanes per block
+  int bx = (g.groups + g.gx - 1) / g.gx;
+  long by = (M + (long)g.gy * 8 - 1) / ((long)g.gy * 8);
+  long cap = (148L * 8 + bx - 1) / bx;
+  if (by > cap) by = cap;
+  if (by < 1) by = 1;
+  g.grid = dim3(bx, (unsigned)by);
+  g.block = dim3(g.gx, g.gy);
+  return g;
+}
+
+// pass 1: per-channel sum / sum of squares (fp32 over short runs, folded into fp64)
+template <int VEC>
 __global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict__ ws, long M, int C) {
-  __shared__ double red[2][8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s = 0.0, ss = 0.0;
+  extern __shared__ double red[];                  // [2][VEC][blockDim.y][blockDim.x]
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = q * VEC;
+  double s[VEC], ss[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s[i] = ss[i] = 0.0;
   if (c < C) {
-    for (long m0 = (long)blockIdx.y * 8 + threadIdx.y; m0 < M; m0 += (long)gridDim.y * 8 * 16) {
-      float ps = 0.f, pss = 0.f;                    // short fp32 runs, folded into fp64
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        long m = m0 + (long)j * gridDim.y * 8;
+    const long step = (long)gridDim.y * blockDim.y;
+    for (long m0 = (long)blockIdx.y * blockDim.y + threadIdx.y; m0 < M; m0 += step * 8) {
+      float ps[VEC], pss[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) ps[i] = pss[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        long m = m0 + j * step;
         if (m < M) {
-          float v = x[m * C + c];
-          ps += v;
-          pss = fmaf(v, v, pss);
+          float v[VEC];
+          ldv<VEC>(x + m * C + c, v);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) { ps[i] += v[i]; pss[i] = fmaf(v[i], v[i], pss[i]); }
         }
       }
-      s += (double)ps;
-      ss += (double)pss;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { s[i] += (double)ps[i]; ss[i] += (double)pss[i]; }
     }
   }
-  red[0][threadIdx.y][threadIdx.x] = s;
-  red[1][threadIdx.y][threadIdx.x] = ss;
+  const int nx = blockDim.x, ny = blockDim.y;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    red[((0 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = s[i];
+    red[((1 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = ss[i];
+  }
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    double a = 0, b = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a += red[0][i][threadIdx.x]; b += red[1][i][threadIdx.x]; }
-    atomicAdd(&ws[c], a);
-    atomicAdd(&ws[C + c], b);
+    for (int i = 0; i < VEC; ++i) {
+      double a = 0, b = 0;
+      for (int r = 0; r < ny; ++r) {
+        a += red[((0 * VEC + i) * ny + r) * nx + threadIdx.x];
+        b += red[((1 * VEC + i) * ny + r) * nx + threadIdx.x];
+      }
+      atomicAdd(&ws[c + i], a);
+      atomicAdd(&ws[C + c + i], b);
+    }
   }
 }
 
@@ -113,61 +162,95 @@ __global__ void bn_finalize_kernel(const double* __restrict__ ws, float* running
   }
 }
 
+template <int VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                 int relu, float* __restrict__ y, long M, int C) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c >= C) return;
-  const float mu = mean[c], rs = rstd[c], g = gamma[c], bt = beta[c];
-  for (long m = blockIdx.y * 8 + threadIdx.y; m < M; m += (long)gridDim.y * 8) {
-    long o = m * C + c;
-    float v = (x[o] - mu) * rs * g + bt;
-    if (res) v += res[o];
-    if (relu) v = fmaxf(v, 0.f);
-    y[o] = v;
+  float mu[VEC], rs[VEC], g[VEC], bt[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { mu[i] = mean[c + i]; rs[i] = rstd[c + i]; g[i] = gamma[c + i]; bt[i] = beta[c + i]; }
+  const long step = (long)gridDim.y * blockDim.y;
+  for (long m = (long)blockIdx.y * blockDim.y + threadIdx.y; m < M; m += step) {
+    float v[VEC], r[VEC];
+    ldv<VEC>(x + m * C + c, v);
+    if (res) ldv<VEC>(res + m * C + c, r);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float o = (v[i] - mu[i]) * rs[i] * g[i] + bt[i];
+      if (res) o += r[i];
+      if (relu) o = fmaxf(o, 0.f);
+      v[i] = o;
+    }
+    stv<VEC>(y + m * C + c, v);
   }
 }
 
 // backward pass 1: sum g, sum g*xhat with g = dy * relu_mask
+template <int VEC>
 __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                      const float* __restrict__ dy, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, int relu,
                                      double* __restrict__ ws, long M, int C) {
-  __shared__ double red[2][8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double s = 0.0, ss = 0.0;
+  extern __shared__ double red[];
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  double s[VEC], ss[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s[i] = ss[i] = 0.0;
   if (c < C) {
-    const float mu = mean[c], rs = rstd[c];
-    for (long m0 = (long)blockIdx.y * 8 + threadIdx.y; m0 < M; m0 += (long)gridDim.y * 8 * 16) {
-      float ps = 0.f, pss = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        long m = m0 + (long)j * gridDim.y * 8;
+    float mu[VEC], rs[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { mu[i] = mean[c + i]; rs[i] = rstd[c + i]; }
+    const long step = (long)gridDim.y * blockDim.y;
+    for (long m0 = (long)blockIdx.y * blockDim.y + threadIdx.y; m0 < M; m0 += step * 4) {
+      float ps[VEC], pss[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) ps[i] = pss[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        long m = m0 + j * step;
         if (m < M) {
-          long o = m * C + c;
-          float g = dy[o];
-          if (relu && !(y[o] > 0.f)) g = 0.f;
-          ps += g;
-          pss = fmaf(g, (x[o] - mu) * rs, pss);
+          float xv[VEC], yv[VEC], gv[VEC];
+          ldv<VEC>(x + m * C + c, xv);
+          ldv<VEC>(dy + m * C + c, gv);
+          if (relu) ldv<VEC>(y + m * C + c, yv);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            float g = gv[i];
+            if (relu && !(yv[i] > 0.f)) g = 0.f;
+            ps[i] += g;
+            pss[i] = fmaf(g, (xv[i] - mu[i]) * rs[i], pss[i]);
+          }
         }
       }
-      s += (double)ps;
-      ss += (double)pss;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { s[i] += (double)ps[i]; ss[i] += (double)pss[i]; }
     }
   }
-  red[0][threadIdx.y][threadIdx.x] = s;
-  red[1][threadIdx.y][threadIdx.x] = ss;
+  const int nx = blockDim.x, ny = blockDim.y;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    red[((0 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = s[i];
+    red[((1 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = ss[i];
+  }
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    double a = 0, b = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a += red[0][i][threadIdx.x]; b += red[1][i][threadIdx.x]; }
-    atomicAdd(&ws[c], a);
-    atomicAdd(&ws[C + c], b);
+    for (int i = 0; i < VEC; ++i) {
+      double a = 0, b = 0;
+      for (int r = 0; r < ny; ++r) {
+        a += red[((0 * VEC + i) * ny + r) * nx + threadIdx.x];
+        b += red[((1 * VEC + i) * ny + r) * nx + threadIdx.x];
+      }
+      atomicAdd(&ws[c + i], a);
+      atomicAdd(&ws[C + c + i], b);
+    }
   }
 }
 
+template <int VEC>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                     const float* __restrict__ dy, const float* __restrict__ gamma,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -175,22 +258,37 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
                                     float* __restrict__ dx, float* __restrict__ dres,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long M,
                                     int C) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c >= C) return;
-  const float mu = mean[c], rs = rstd[c], gm = gamma[c];
-  const float sg = (float)ws[c], sgx = (float)ws[C + c];
-  const float k1 = training ? sg / (float)M : 0.f, k2 = training ? sgx / (float)M : 0.f;
-  if (blockIdx.y == 0 && threadIdx.y == 0) {
-    if (dgamma) dgamma[c] = sgx;
-    if (dbeta) dbeta[c] = sg;
+  float mu[VEC], rs[VEC], gm[VEC], k1[VEC], k2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    mu[i] = mean[c + i]; rs[i] = rstd[c + i]; gm[i] = gamma[c + i];
+    const float sg = (float)ws[c + i], sgx = (float)ws[C + c + i];
+    k1[i] = training ? sg / (float)M : 0.f;
+    k2[i] = training ? sgx / (float)M : 0.f;
+    if (blockIdx.y == 0 && threadIdx.y == 0) {
+      if (dgamma) dgamma[c + i] = sgx;
+      if (dbeta) dbeta[c + i] = sg;
+    }
   }
-  for (long m = blockIdx.y * 8 + threadIdx.y; m < M; m += (long)gridDim.y * 8) {
-    long o = m * C + c;
-    float g = dy[o];
-    if (relu && !(y[o] > 0.f)) g = 0.f;
-    if (dres) dres[o] = g;
-    float xh = (x[o] - mu) * rs;
-    dx[o] = gm * rs * (g - k1 - xh * k2);
+  const long step = (long)gridDim.y * blockDim.y;
+  for (long m = (long)blockIdx.y * blockDim.y + threadIdx.y; m < M; m += step) {
+    float xv[VEC], yv[VEC], gv[VEC];
+    ldv<VEC>(x + m * C + c, xv);
+    ldv<VEC>(dy + m * C + c, gv);
+    if (relu) ldv<VEC>(y + m * C + c, yv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (relu && !(yv[i] > 0.f)) gv[i] = 0.f;
+    }
+    if (dres) stv<VEC>(dres + m * C + c, gv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float xh = (xv[i] - mu[i]) * rs[i];
+      xv[i] = gm[i] * rs[i] * (gv[i] - k1[i] - xh * k2[i]);
+    }
+    stv<VEC>(dx + m * C + c, xv);
   }
 }
 
@@ -405,16 +503,22 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(fd::cdiv(C, 32), pix_chunks(M)), blk(32, 8);
+  const int vec = (C % 4 == 0) ? 4 : 1;
+  BnGeom g = bn_geom(M, C, vec);
+  const size_t sm = sizeof(double) * 2 * vec * 256;
   if (training) {
     cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
-    bn_stats_kernel<<<grid, blk, 0, st>>>(x, ws, M, C);
+    if (vec == 4) bn_stats_kernel<4><<<g.grid, g.block, sm, st>>>(x, ws, M, C);
+    else bn_stats_kernel<1><<<g.grid, g.block, sm, st>>>(x, ws, M, C);
     FD_CHECK_LAUNCH();
   }
   bn_finalize_kernel<<<fd::cdiv(C, 128), 128, 0, st>>>(ws, running_mean, running_var, training,
                                                        momentum, eps, save_mean, save_rstd, M, C);
   FD_CHECK_LAUNCH();
-  bn_apply_kernel<<<grid, blk, 0, st>>>(x, residual, gamma, beta, save_mean, save_rstd, relu, y, M, C);
+  if (vec == 4)
+    bn_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, save_mean, save_rstd, relu, y, M, C);
+  else
+    bn_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, save_mean, save_rstd, relu, y, M, C);
   FD_CHECK_LAUNCH();
   return 0;
 }
@@ -424,12 +528,21 @@ int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
               float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(fd::cdiv(C, 32), pix_chunks(M)), blk(32, 8);
+  const int vec = (C % 4 == 0) ? 4 : 1;
+  BnGeom g = bn_geom(M, C, vec);
+  const size_t sm = sizeof(double) * 2 * vec * 256;
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
-  bn_bwd_reduce_kernel<<<grid, blk, 0, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
-  FD_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<grid, blk, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training, ws,
-                                            dx, dresidual, dgamma, dbeta, M, C);
+  if (vec == 4) {
+    bn_bwd_reduce_kernel<4><<<g.grid, g.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
+    FD_CHECK_LAUNCH();
+    bn_bwd_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
+                                                       ws, dx, dresidual, dgamma, dbeta, M, C);
+  } else {
+    bn_bwd_reduce_kernel<1><<<g.grid, g.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
+    FD_CHECK_LAUNCH();
+    bn_bwd_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
+                                                       ws, dx, dresidual, dgamma, dbeta, M, C);
+  }
   FD_CHECK_LAUNCH();
   return 0;
 }

@@ -372,20 +372,33 @@ struct SmArgs {
   int B, H, W;
   const float* disp[4];
   const float* color[4];
-  float* mean;        // [B][4]
+  float* mean;        // [B*4][SM_CHUNKS] partial sums of disp
   float* sm_partial;  // [B*4][SM_CHUNKS][2]
 };
 constexpr int SM_CHUNKS = 32;
 
 __global__ void disp_mean_kernel(SmArgs a) {
+  // partial sums of disp over SM_CHUNKS blocks per (image, scale); block_mean() finishes them
   __shared__ double red[32];
-  const int b = blockIdx.x >> 2, s = blockIdx.x & 3;
+  const int b = blockIdx.y >> 2, s = blockIdx.y & 3;
   const int n = (a.H >> s) * (a.W >> s);
   const float* d = a.disp[s] + (long)b * n;
   double acc[1] = {0.0};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc[0] += (double)d[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc[0] += (double)d[i];
   fd::block_sum<1>(acc, red);
-  if (threadIdx.x == 0) a.mean[b * 4 + s] = (float)(acc[0] / (double)n);
+  if (threadIdx.x == 0) a.mean[(long)blockIdx.y * SM_CHUNKS + blockIdx.x] = (float)acc[0];
+}
+
+// mean of disp_s of image b from the partial sums (fixed order => deterministic), for the whole block
+__device__ float block_mean(const float* __restrict__ mpart, int bs, int n) {
+  __shared__ float mean_sh;
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int c = 0; c < SM_CHUNKS; ++c) t += (double)mpart[(long)bs * SM_CHUNKS + c];
+    mean_sh = (float)(t / (double)n);
+  }
+  __syncthreads();
+  return mean_sh;
 }
 
 // edge-aware smoothness partial sums   (layers.py:235-248 on norm_disp, trainer.py:570-571)
@@ -395,7 +408,7 @@ __global__ void smooth_fwd_kernel(SmArgs a) {
   const int h = a.H >> s, w = a.W >> s, n = h * w;
   const float* d = a.disp[s] + (long)b * n;
   const float* img = a.color[s] + (long)b * 3 * n;
-  const float den = __fadd_rn(a.mean[b * 4 + s], 1e-7f);
+  const float den = __fadd_rn(block_mean(a.mean, blockIdx.y, n), 1e-7f);
   double acc[2] = {0.0, 0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int y = i / w, x = i % w;
@@ -714,7 +727,7 @@ struct DGArgs {
   const float* disp[4];
   const float* color[4];
   const float* gd_up[4];
-  const float* mean;     // [B][4]
+  const float* mean;     // [B*4][SM_CHUNKS] partial sums of disp
   const float* stats;
   const float* gout;
   float smooth_w;
@@ -730,7 +743,7 @@ __global__ void disp_grad_kernel(DGArgs a) {
   const float* d = a.disp[s] + (long)b * n;
   const float* img = a.color[s] + (long)b * 3 * n;
   const float* gu = a.gd_up[s] + (long)b * H * W;
-  const float den = __fadd_rn(a.mean[b * 4 + s], 1e-7f);
+  const float den = __fadd_rn(block_mean(a.mean, blockIdx.y, n), 1e-7f);
   const float Lb = a.stats[16 + b * 4 + s];
   const float gs = a.gout[0] * 0.25f * a.smooth_w / (float)r;
   const float inx = 1.f / ((float)a.B * h * (w - 1)), iny = 1.f / ((float)a.B * (h - 1) * w);
@@ -829,11 +842,11 @@ int fill_args(PLArgs& a, const fd_photoloss_desc* d) {
 
 extern "C" {
 
-// workspace layout (floats): [partial fwd nblk*16][sm_partial B*4*32*2][mean B*4][stats 16+B*4]
+// workspace layout (floats): [partial fwd nblk*16][sm_partial B*4*32*2][disp partial sums B*4*32][stats 16+B*4]
 //                            [partial_dP nblk*24][gd_up 4*B*H*W]
 size_t fd_photoloss_workspace_bytes(int B, int H, int W) {
   long nblk = (long)fd::cdiv(W, TX) * fd::cdiv(H, TY) * B;
-  long fl = nblk * NPART + (long)B * 4 * SM_CHUNKS * 2 + B * 4 + 16 + B * 4 + nblk * NPART_B +
+  long fl = nblk * NPART + (long)B * 4 * SM_CHUNKS * 2 + (long)B * 4 * SM_CHUNKS + 16 + B * 4 + nblk * NPART_B +
             4L * B * H * W;
   return (size_t)fl * sizeof(float);
 }
@@ -848,7 +861,7 @@ static WsView ws_view(void* ws, int B, int H, int W) {
   float* p = (float*)ws;
   v.partial = p; p += v.nblk * NPART;
   v.sm_partial = p; p += (long)B * 4 * SM_CHUNKS * 2;
-  v.mean = p; p += B * 4;
+  v.mean = p; p += (long)B * 4 * SM_CHUNKS;
   v.stats = p; p += 16 + B * 4;
   v.partial_dP = p; p += v.nblk * NPART_B;
   v.gd_up = p;
@@ -868,7 +881,7 @@ int fd_photoloss_fwd(const fd_photoloss_desc* d, float* losses, void* workspace,
   sa.B = d->B; sa.H = d->H; sa.W = d->W;
   for (int s = 0; s < 4; ++s) { sa.disp[s] = a.disp[s]; sa.color[s] = a.color[s]; }
   sa.mean = v.mean; sa.sm_partial = v.sm_partial;
-  disp_mean_kernel<<<d->B * 4, 256, 0, st>>>(sa);
+  disp_mean_kernel<<<dim3(SM_CHUNKS, d->B * 4), 256, 0, st>>>(sa);
   FD_CHECK_LAUNCH();
   smooth_fwd_kernel<<<dim3(SM_CHUNKS, d->B * 4), 256, 0, st>>>(sa);
   FD_CHECK_LAUNCH();
