@@ -57,6 +57,8 @@ _SIGNATURES = {
     "fd_photoloss_fwd": (c_int, [POINTER(PhotolossDesc), _P, _P, _P]),
     "fd_photoloss_bwd": (c_int, [POINTER(PhotolossDesc), _P, POINTER(c_void_p * 4), _P, _P, _P, _P]),
     "fd_prep_input": (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
+    "fd_stem_im2col": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "fd_pad_rows": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "fd_conv2d_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_dgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_wgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

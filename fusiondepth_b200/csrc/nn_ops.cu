@@ -32,6 +32,43 @@ __global__ void prep_input_kernel(const float* __restrict__ x, float* __restrict
     y[((long)b * HW + p) * C + c] = __fdiv_rn(__fadd_rn(x[((long)b * C + c) * HW + p], -mean), stdv);
 }
 
+// ---- 7x7/2 stem as a GEMM: normalised im2col rows ------------------------------------------------
+// A[m][k], m = (b,ho,wo), k = (kh*KW + kw)*C + c for k < KH*KW*C, zero up to Kpad (a multiple of 32 so
+// the tensor-core 1x1 path takes it).  Values are (x - mean)/std inside the image, 0 in the padding.
+__global__ void stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ A, int C, int H, int W,
+                                   int Ho, int Wo, int KH, int KW, int stride, int pad, int Kpad,
+                                   float mean, float stdv, long total) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int k = (int)(i % Kpad);
+    long m = i / Kpad;
+    float v = 0.f;
+    if (k < KH * KW * C) {
+      int c = k % C, tap = k / C;
+      int kh = tap / KW, kw = tap - kh * KW;
+      int wo = (int)(m % Wo);
+      long t = m / Wo;
+      int ho = (int)(t % Ho), b = (int)(t / Ho);
+      int h = ho * stride - pad + kh, w = wo * stride - pad + kw;
+      if (h >= 0 && h < H && w >= 0 && w < W)
+        v = __fdiv_rn(__fadd_rn(x[(((long)b * C + c) * H + h) * W + w], -mean), stdv);
+    }
+    A[i] = v;
+  }
+}
+
+// dst[r][0..cols_dst) = src[r][0..cols_src) zero-padded (cols_dst >= cols_src), or the reverse
+// accumulate (unpad: dst[r][c] += src[r][c] for c < cols_dst)
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols_src,
+                                int cols_dst, int accumulate) {
+  long n = (long)rows * cols_dst;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cols_dst);
+    long r = i / cols_dst;
+    float v = c < cols_src ? src[r * cols_src + c] : 0.f;
+    if (accumulate) dst[i] += v; else dst[i] = v;
+  }
+}
+
 // ---- activation backward + bias gradient ---------------------------------------------------
 // grid.x covers channel groups of 32, grid.y pixel chunks; block (32, 8)
 __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
@@ -486,6 +523,26 @@ int fd_prep_input(const float* x, float* y, int B, int C, int H, int W, float me
                   void* stream) {
   prep_input_kernel<<<dim3(fd::cdiv((long)H * W, 256), B), 256, 0, (cudaStream_t)stream>>>(
       x, y, C, H * W, mean, stdv);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_stem_im2col(const float* x_nchw, float* A, int B, int C, int H, int W, int KH, int KW, int stride,
+                   int pad, int Kpad, float mean, float stdv, void* stream) {
+  FD_REQUIRE(Kpad >= KH * KW * C && Kpad % 4 == 0, "fd_stem_im2col: bad Kpad %d", Kpad);
+  int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  long total = (long)B * Ho * Wo * Kpad;
+  stem_im2col_kernel<<<min(fd::cdiv(total, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      x_nchw, A, C, H, W, Ho, Wo, KH, KW, stride, pad, Kpad, mean, stdv, total);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_pad_rows(const float* src, float* dst, int rows, int cols_src, int cols_dst, int accumulate,
+                void* stream) {
+  long n = (long)rows * cols_dst;
+  pad_rows_kernel<<<min(fd::cdiv(n, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, cols_src,
+                                                                                  cols_dst, accumulate);
   FD_CHECK_LAUNCH();
   return 0;
 }

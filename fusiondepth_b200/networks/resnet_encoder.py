@@ -154,8 +154,8 @@ class ResnetEncoder(nn.Module):
     def forward(self, input_image):
         enc = self.encoder
         self.features = []
-        x = ops.prep_input(input_image)                        # (x - 0.45) / 0.225, NHWC
-        self.features.append(enc.bn1(enc.conv1(x), relu=True))
+        # (x - 0.45) / 0.225 and the 7x7/2 stem in one op (normalised im2col rows -> GEMM)
+        self.features.append(enc.bn1(ops.stem_conv(input_image, enc.conv1.weight), relu=True))
         x = ops.maxpool3x3s2(self.features[-1])
         for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
             for blk in layer:

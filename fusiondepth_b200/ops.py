@@ -178,6 +178,66 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, act="none"):
 
 
 # --------------------------------------------------------------------------------------------
+class StemConvFn(torch.autograd.Function):
+    """conv1 of the ResNet trunks (7x7/2, pad 3, Cin 2..6, no bias) with the input normalisation
+    folded in: normalised im2col rows -> tensor-core GEMM (resnet_encoder.py:94-95).  The image
+    carries no gradient; the weight gradient is a tensor-core GEMM over the saved rows."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        _require_cuda(x, "stem_conv")
+        lib = _lib.load()
+        x = x.contiguous()
+        w = nhwc(weight)
+        B, C, H, W = x.shape
+        Cout, Cw, KH, KW = w.shape
+        if Cw != C:
+            raise RuntimeError("stem_conv: input has %d channels, weight expects %d" % (C, Cw))
+        stride, pad = 2, 3
+        Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+        K = KH * KW * C
+        Kpad = (K + 31) // 32 * 32
+        st = _stream()
+        A = torch.empty((B * Ho * Wo, Kpad), device=x.device, dtype=torch.float32)
+        _lib.check(lib.fd_stem_im2col(_p(x), _p(A), B, C, H, W, KH, KW, stride, pad, Kpad, 0.45, 0.225, st),
+                   "fd_stem_im2col")
+        wpad = torch.empty((Cout, Kpad), device=x.device, dtype=torch.float32)
+        _lib.check(lib.fd_pad_rows(_p(w), _p(wpad), Cout, K, Kpad, 0, st), "fd_pad_rows")
+        wlo = torch.empty_like(wpad)
+        _lib.check(lib.fd_tf32_split(_p(wpad), _p(wlo), wpad.numel(), st), "fd_tf32_split")
+        y = empty_nhwc(B, Cout, Ho, Wo, x.device)
+        with _timed("conv", 2.0 * B * Ho * Wo * Cout * K):
+            _lib.check(lib.fd_conv2d_fwd_tc(_p(A), _p(wpad), _p(wlo), None, _p(y), B, Ho, Wo, Kpad, Cout,
+                                            1, 1, 1, 0, 0, st), "fd_conv2d_fwd_tc")
+        ctx.save_for_backward(A)
+        ctx.cfg = (B, Ho, Wo, Kpad, Cout, C, KH, KW, K)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (A,) = ctx.saved_tensors
+        B, Ho, Wo, Kpad, Cout, C, KH, KW, K = ctx.cfg
+        dy = nhwc(dy)
+        st = _stream()
+        dwpad = torch.zeros((Cout, Kpad), device=dy.device, dtype=torch.float32)
+        with _timed("conv", 2.0 * B * Ho * Wo * Cout * K):
+            _lib.check(lib.fd_conv2d_wgrad_tc(_p(A), _p(dy), _p(dwpad), B, Ho, Wo, Kpad, Cout, 1, 1, 1, 0, st),
+                       "fd_conv2d_wgrad_tc")
+        dw = torch.empty((Cout, C, KH, KW), device=dy.device, dtype=torch.float32, memory_format=CL)
+        _lib.check(lib.fd_pad_rows(_p(dwpad), _p(dw), Cout, Kpad, K, 0, st), "fd_pad_rows")
+        return None, dw
+
+
+def stem_conv(x, weight):
+    """(x-0.45)/0.225 -> 7x7/2 conv, NHWC output.  Tensor-core path when enabled."""
+    Cout, C, KH, KW = weight.shape
+    if CONV_BACKEND == "tc" and (KH, KW) == (7, 7) and Cout % 32 == 0:
+        return StemConvFn.apply(x, weight)
+    return conv2d(prep_input(x), weight, None, 2, 3, "none")
+
+
+# --------------------------------------------------------------------------------------------
 class BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps,

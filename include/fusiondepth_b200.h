@@ -102,6 +102,16 @@ enum { FD_ACT_NONE = 0, FD_ACT_RELU = 1, FD_ACT_ELU = 2, FD_ACT_SIGMOID = 3, FD_
 int fd_prep_input(const float* x_nchw, float* y_nhwc, int B, int C, int H, int W, float mean,
                   float std, void* stream);
 
+/* The 7x7/2 stem as a GEMM (resnet_encoder.py:94-95): A [B*Ho*Wo, Kpad] = normalised im2col rows of
+ * the NCHW input, k = (kh*KW+kw)*C + c, zero-filled up to Kpad (multiple of 32), so that the
+ * tensor-core 1x1 path (fd_conv2d_fwd_tc / fd_conv2d_wgrad_tc on [B,Ho,Wo,Kpad]) runs it.
+ * fd_pad_rows pads weight rows [rows,cols_src] -> [rows,cols_dst] (accumulate=0), or folds a padded
+ * gradient back (cols_dst < cols_src, accumulate=1). */
+int fd_stem_im2col(const float* x_nchw, float* A, int B, int C, int H, int W, int KH, int KW, int stride,
+                   int pad, int Kpad, float mean, float std, void* stream);
+int fd_pad_rows(const float* src, float* dst, int rows, int cols_src, int cols_dst, int accumulate,
+                void* stream);
+
 /* y = act(conv(x, w) + bias); zero padding `pad`.  x [B,H,W,Cin], w [Cout,KH,KW,Cin],
  * y [B,Ho,Wo,Cout], Ho = (H+2*pad-KH)/stride+1. */
 int fd_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,

@@ -199,3 +199,21 @@ def test_conv_tensor_core_vs_exact_fp32(cuda, case):
     print("conv %s  fwd err tc %.2e fp32 %.2e | dgrad tc %.2e fp32 %.2e | wgrad tc %.2e fp32 %.2e"
           % (case, e_tc[0], e_cc[0], e_tc[1], e_cc[1], e_tc[2], e_cc[2]))
     assert e_tc[0] < 5e-6 and e_tc[1] < 5e-6 and e_tc[2] < 2e-5, (e_tc, e_cc)
+
+
+@pytest.mark.parametrize("C", [3, 2, 6, 4])
+def test_stem_conv(cuda, C):
+    """(x-0.45)/0.225 -> 7x7/2 conv through normalised im2col rows + tensor-core GEMM"""
+    from fusiondepth_b200 import ops
+    x = torch.rand(2, C, 64, 96, generator=torch.Generator().manual_seed(C))
+    w = _rand((64, C, 7, 7), 5, (1.0 / (C * 49)) ** 0.5)
+    wr = w.double().requires_grad_(True)
+    ref = F.conv2d((x.double() - 0.45) / 0.225, wr, None, 2, 3)
+    gy = _rand(tuple(ref.shape), 6)
+    ref.backward(gy.double())
+    wc = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    y = ops.stem_conv(x.cuda(), wc)
+    y.backward(gy.cuda())
+    assert rel_err(y.detach().cpu(), ref.detach()) < 5e-6
+    assert rel_err(wc.grad.cpu(), wr.grad) < 2e-5
+    assert wc.grad.is_contiguous(memory_format=CL)
