@@ -71,7 +71,7 @@ _SIGNATURES = {
     "fd_conv2d_wgrad_tc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_act_bwd": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P]),
     "fd_bn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P, _L, _I, _P]),
-    "fd_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "fd_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "fd_maxpool3x3s2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_maxpool3x3s2_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_assemble_fwd": (c_int, [POINTER(Segment), _I, _P, _I, _I, _I, _I, _P]),

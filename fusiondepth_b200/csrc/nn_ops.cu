@@ -65,7 +65,7 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict
     int c = (int)(i % cols_dst);
     long r = i / cols_dst;
     float v = c < cols_src ? src[r * cols_src + c] : 0.f;
-    if (accumulate) dst[i] += v; else dst[i] = v;
+    if (accumulate) atomicAdd(&dst[i], v); else dst[i] = v;
   }
 }
 
@@ -294,7 +294,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
                                     int relu, int training, const double* __restrict__ ws,
                                     float* __restrict__ dx, float* __restrict__ dres,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long M,
-                                    int C) {
+                                    int C, int accumulate) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c >= C) return;
   float mu[VEC], rs[VEC], gm[VEC], k1[VEC], k2[VEC];
@@ -305,8 +305,13 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
     k1[i] = training ? sg / (float)M : 0.f;
     k2[i] = training ? sgx / (float)M : 0.f;
     if (blockIdx.y == 0 && threadIdx.y == 0) {
-      if (dgamma) dgamma[c + i] = sgx;
-      if (dbeta) dbeta[c + i] = sg;
+      if (accumulate) {                 // several streams may add into the same parameter gradient
+        if (dgamma) atomicAdd(&dgamma[c + i], sgx);
+        if (dbeta) atomicAdd(&dbeta[c + i], sg);
+      } else {
+        if (dgamma) dgamma[c + i] = sgx;
+        if (dbeta) dbeta[c + i] = sg;
+      }
     }
   }
   const long step = (long)gridDim.y * blockDim.y;
@@ -583,7 +588,7 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
 int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
               const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
               float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
-              void* stream) {
+              int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int vec = (C % 4 == 0) ? 4 : 1;
   BnGeom g = bn_geom(M, C, vec);
@@ -593,12 +598,12 @@ int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
     bn_bwd_reduce_kernel<4><<<g.grid, g.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
     FD_CHECK_LAUNCH();
     bn_bwd_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
-                                                       ws, dx, dresidual, dgamma, dbeta, M, C);
+                                                       ws, dx, dresidual, dgamma, dbeta, M, C, accumulate);
   } else {
     bn_bwd_reduce_kernel<1><<<g.grid, g.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
     FD_CHECK_LAUNCH();
     bn_bwd_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
-                                                       ws, dx, dresidual, dgamma, dbeta, M, C);
+                                                       ws, dx, dresidual, dgamma, dbeta, M, C, accumulate);
   }
   FD_CHECK_LAUNCH();
   return 0;

@@ -18,6 +18,39 @@ from . import _lib
 ACT = {"none": 0, "relu": 1, "elu": 2, "sigmoid": 3, "tanh": 4}
 # "tc": tcgen05 tensor-core convolutions wherever eligible (default); "cudacore": exact-fp32 path
 CONV_BACKEND = os.environ.get("FD_CONV", "tc")
+
+# Set by training.TrainStep: parameters carry a preallocated gradient view (`p._fd_grad`, a slice of
+# the flat gradient buffer) and the backward kernels add into it directly (the weight-gradient and
+# bias kernels accumulate with reductions anyway), so autograd's AccumulateGrad pass and the zeroed
+# temporaries disappear.
+DIRECT_GRAD = False
+
+# Per-step cache of derived weight tensors (W_lo, transposed W / W_lo, padded stem weights), keyed by
+# the weight's address.  TrainStep clears it at the start of every optimiser step; entries carry the
+# event of the stream that produced them so other trunk streams can wait on it.
+WEIGHT_CACHE: Optional[Dict] = None
+
+
+def _direct_grad(p):
+    return getattr(p, "_fd_grad", None) if (DIRECT_GRAD and p is not None) else None
+
+
+def _cached(key, make):
+    """make() -> tuple of tensors, computed once per step when the cache is on."""
+    if WEIGHT_CACHE is None:
+        return make()
+    hit = WEIGHT_CACHE.get(key)
+    cur = torch.cuda.current_stream()
+    if hit is None:
+        val = make()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        WEIGHT_CACHE[key] = (val, ev, cur)
+        return val
+    val, ev, owner = hit
+    if owner != cur:
+        cur.wait_event(ev)
+    return val
 CL = torch.channels_last
 
 
@@ -111,8 +144,11 @@ class Conv2dFn(torch.autograd.Function):
         y = empty_nhwc(B, Cout, Ho, Wo, x.device)
         use_tc = CONV_BACKEND == "tc" and Cin % 32 == 0 and Cout % 16 == 0
         if use_tc:
-            wlo = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
-            _lib.check(lib.fd_tf32_split(_p(w), _p(wlo), w.numel(), _stream()), "fd_tf32_split")
+            def make_lo():
+                t = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
+                _lib.check(lib.fd_tf32_split(_p(w), _p(t), w.numel(), _stream()), "fd_tf32_split")
+                return (t,)
+            (wlo,) = _cached((w.data_ptr(), "lo"), make_lo)
             with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
                 _lib.check(lib.fd_conv2d_fwd_tc(_p(x), _p(w), _p(wlo), _p(bias), _p(y), B, H, W, Cin,
                                                 Cout, KH, KW, stride, pad, act, _stream()),
@@ -123,6 +159,7 @@ class Conv2dFn(torch.autograd.Function):
                                              stride, pad, act, _stream()), "fd_conv2d_fwd")
         ctx.save_for_backward(x, w, y if act != 0 else None)
         ctx.cfg = (stride, pad, act, bias is not None)
+        ctx.wg, ctx.bg = _direct_grad(weight), _direct_grad(bias)
         return y
 
     @staticmethod
@@ -137,7 +174,8 @@ class Conv2dFn(torch.autograd.Function):
         st = _stream()
         dbias = None
         if act != 0 or has_bias:
-            dbias = torch.zeros(Cout, device=x.device, dtype=torch.float32) if has_bias else None
+            if has_bias:
+                dbias = ctx.bg if ctx.bg is not None else torch.zeros(Cout, device=x.device, dtype=torch.float32)
             dpre = torch.empty_like(dy) if act != 0 else dy
             _lib.check(lib.fd_act_bwd(_p(y if act != 0 else dy), _p(dy), _p(dpre), _p(dbias), M, Cout,
                                       act, st), "fd_act_bwd")
@@ -147,9 +185,13 @@ class Conv2dFn(torch.autograd.Function):
             wt = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
             dx = empty_nhwc(B, Cin, H, W, x.device)
             if CONV_BACKEND == "tc" and Cout % 32 == 0 and Cin % 16 == 0:
-                wtlo = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
-                _lib.check(lib.fd_weight_transpose_split(_p(w), _p(wt), _p(wtlo), Cout, KH * KW, Cin, st),
-                           "fd_weight_transpose_split")
+                def make_t():
+                    a = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
+                    b = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
+                    _lib.check(lib.fd_weight_transpose_split(_p(w), _p(a), _p(b), Cout, KH * KW, Cin,
+                                                             _stream()), "fd_weight_transpose_split")
+                    return a, b
+                wt, wtlo = _cached((w.data_ptr(), "t"), make_t)
                 with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
                     _lib.check(lib.fd_conv2d_dgrad_tc(_p(dy), _p(wt), _p(wtlo), _p(dx), B, H, W, Cin,
                                                       Cout, KH, KW, stride, pad, st), "fd_conv2d_dgrad_tc")
@@ -161,8 +203,8 @@ class Conv2dFn(torch.autograd.Function):
                                                    stride, pad, st), "fd_conv2d_dgrad")
         dw = None
         if ctx.needs_input_grad[1]:
-            dw = torch.empty((Cout, Cin, KH, KW), device=x.device, dtype=torch.float32,
-                             memory_format=CL).zero_()
+            dw = ctx.wg if ctx.wg is not None else torch.empty(
+                (Cout, Cin, KH, KW), device=x.device, dtype=torch.float32, memory_format=CL).zero_()
             with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
                 if CONV_BACKEND == "tc" and Cin % 32 == 0 and Cout % 32 == 0:
                     _lib.check(lib.fd_conv2d_wgrad_tc(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
@@ -170,7 +212,9 @@ class Conv2dFn(torch.autograd.Function):
                 else:
                     _lib.check(lib.fd_conv2d_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
                                                    stride, pad, st), "fd_conv2d_wgrad")
-        return dx, dw, dbias, None, None, None
+        # gradients written straight into the parameters' buffers are not handed back to autograd
+        return (dx, None if ctx.wg is not None else dw, None if ctx.bg is not None else dbias,
+                None, None, None)
 
 
 def conv2d(x, weight, bias=None, stride=1, pad=0, act="none"):
@@ -201,16 +245,20 @@ class StemConvFn(torch.autograd.Function):
         A = torch.empty((B * Ho * Wo, Kpad), device=x.device, dtype=torch.float32)
         _lib.check(lib.fd_stem_im2col(_p(x), _p(A), B, C, H, W, KH, KW, stride, pad, Kpad, 0.45, 0.225, st),
                    "fd_stem_im2col")
-        wpad = torch.empty((Cout, Kpad), device=x.device, dtype=torch.float32)
-        _lib.check(lib.fd_pad_rows(_p(w), _p(wpad), Cout, K, Kpad, 0, st), "fd_pad_rows")
-        wlo = torch.empty_like(wpad)
-        _lib.check(lib.fd_tf32_split(_p(wpad), _p(wlo), wpad.numel(), st), "fd_tf32_split")
+        def make_pad():
+            a = torch.empty((Cout, Kpad), device=x.device, dtype=torch.float32)
+            _lib.check(lib.fd_pad_rows(_p(w), _p(a), Cout, K, Kpad, 0, _stream()), "fd_pad_rows")
+            b = torch.empty_like(a)
+            _lib.check(lib.fd_tf32_split(_p(a), _p(b), a.numel(), _stream()), "fd_tf32_split")
+            return a, b
+        wpad, wlo = _cached((w.data_ptr(), "stem"), make_pad)
         y = empty_nhwc(B, Cout, Ho, Wo, x.device)
         with _timed("conv", 2.0 * B * Ho * Wo * Cout * K):
             _lib.check(lib.fd_conv2d_fwd_tc(_p(A), _p(wpad), _p(wlo), None, _p(y), B, Ho, Wo, Kpad, Cout,
                                             1, 1, 1, 0, 0, st), "fd_conv2d_fwd_tc")
         ctx.save_for_backward(A)
         ctx.cfg = (B, Ho, Wo, Kpad, Cout, C, KH, KW, K)
+        ctx.wg = _direct_grad(weight)
         return y
 
     @staticmethod
@@ -224,6 +272,9 @@ class StemConvFn(torch.autograd.Function):
         with _timed("conv", 2.0 * B * Ho * Wo * Cout * K):
             _lib.check(lib.fd_conv2d_wgrad_tc(_p(A), _p(dy), _p(dwpad), B, Ho, Wo, Kpad, Cout, 1, 1, 1, 0, st),
                        "fd_conv2d_wgrad_tc")
+        if ctx.wg is not None:
+            _lib.check(lib.fd_pad_rows(_p(dwpad), _p(ctx.wg), Cout, Kpad, K, 1, st), "fd_pad_rows")
+            return None, None
         dw = torch.empty((Cout, C, KH, KW), device=dy.device, dtype=torch.float32, memory_format=CL)
         _lib.check(lib.fd_pad_rows(_p(dwpad), _p(dw), Cout, Kpad, K, 0, st), "fd_pad_rows")
         return None, dw
@@ -258,6 +309,7 @@ class BatchNormFn(torch.autograd.Function):
                                  _p(mean), _p(rstd), _p(ws), M, C, _stream()), "fd_bn_fwd")
         ctx.save_for_backward(x, y, gamma, mean, rstd)
         ctx.cfg = (int(relu), int(training), residual is not None)
+        ctx.gg, ctx.gb = _direct_grad(gamma), _direct_grad(beta)
         return y
 
     @staticmethod
@@ -270,12 +322,15 @@ class BatchNormFn(torch.autograd.Function):
         M = B * H * W
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
-        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
-        dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
+        direct = ctx.gg is not None and ctx.gb is not None
+        dgamma = ctx.gg if direct else torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = ctx.gb if direct else torch.empty(C, device=x.device, dtype=torch.float32)
         ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
         _lib.check(lib.fd_bn_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(mean), _p(rstd), relu, training,
-                                 _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, _stream()),
-                   "fd_bn_bwd")
+                                 _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, int(direct),
+                                 _stream()), "fd_bn_bwd")
+        if direct:
+            return dx, None, None, None, None, dres, None, None, None, None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
 
 

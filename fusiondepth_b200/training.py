@@ -212,6 +212,7 @@ class FlatParams:
             dv.copy_(p.data)
             p.data = dv
             p.grad = gv
+            p._fd_grad = gv          # ops.DIRECT_GRAD: backward kernels add into this view
             off += (k + A - 1) // A * A
         self.numel = n
 
@@ -242,7 +243,8 @@ class TrainStep:
     gradient buffer is averaged across ranks with one NCCL all-reduce before Adam."""
 
     def __init__(self, models, lr: float = 1e-4, accumulate: int = 1, opts: Optional[Dict] = None,
-                 process_group=None, parallel_trunks: bool = True):
+                 process_group=None, parallel_trunks: bool = True, direct_grad: bool = True,
+                 cache_weight_prep: bool = True):
         self.models = models
         self.accumulate = accumulate
         self.lr = float(lr)
@@ -256,6 +258,7 @@ class TrainStep:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        self.direct_grad, self.cache_weight_prep = direct_grad, cache_weight_prep
         self.streams = TrunkStreams(dev) if parallel_trunks else None
         self.stream = torch.cuda.Stream(device=dev)      # warm-up and capture share one stream
         self.graph = None
@@ -268,11 +271,24 @@ class TrainStep:
     # -- eager -------------------------------------------------------------------------------
     def _run(self, batches: Sequence[Dict], noises: Sequence[Dict]):
         self.flat.zero_grad()
+        ops.DIRECT_GRAD = self.direct_grad
+        ops.WEIGHT_CACHE = {} if self.cache_weight_prep else None
+        try:
+            return self._run_inner(batches, noises)
+        finally:
+            ops.DIRECT_GRAD = False
+            ops.WEIGHT_CACHE = None
+
+    def _run_inner(self, batches: Sequence[Dict], noises: Sequence[Dict]):
         total = None
         for inputs, noise in zip(batches, noises):
             _, losses = process_batch(self.models, inputs, noise, self.opts, streams=self.streams)
             loss = losses["loss"] / self.accumulate
             loss.backward()
+            if self.streams is not None:
+                # direct gradient accumulation bypasses AccumulateGrad, so autograd has no leaf
+                # streams to join: wait for every trunk stream's backward kernels explicitly
+                self.streams.join(range(len(self.streams.side)))
             total = loss.detach() if total is None else total + loss.detach()
         reduce_gradients(self.flat, self.world, self.pg)
         ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.adam_state,

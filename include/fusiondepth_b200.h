@@ -147,7 +147,8 @@ int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long 
 
 /* BatchNorm2d (+ optional residual add, + optional ReLU) over M = B*H*W rows of C channels.
  * training: batch statistics, running stats updated (momentum, unbiased var).
- * ws: 2*C doubles of scratch.  save_mean/save_rstd [C] are outputs used by the backward. */
+ * ws: 2*C doubles of scratch.  save_mean/save_rstd [C] are outputs used by the backward.
+ * accumulate_param_grads: dgamma/dbeta are added (atomically) into existing buffers instead of set. */
 int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
               float* running_mean, float* running_var, int training, float momentum, float eps,
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
@@ -155,7 +156,7 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
 int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
               const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
               float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
-              void* stream);
+              int accumulate_param_grads, void* stream);
 
 /* nn.MaxPool2d(3, 2, 1)  (ResNet stem) */
 int fd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C,
