@@ -1,0 +1,314 @@
+// Implicit-GEMM convolution (forward / data gradient) on tcgen05 with the A operand in TENSOR MEMORY.
+//
+// Same contract and numerics as conv_tc.cu (3xTF32: corr += A_lo*B + A*B_lo, main_i += A*B), but the
+// im2col tile never goes back to shared memory after the split:
+//
+//   warps 0-3   loaders    cp.async zero-fill gather of the [128 px x 32 ch] im2col tile into a
+//                          SWIZZLE_128B shared stage; one thread fetches the W / W_lo tiles by TMA;
+//   warps 4-11  splitters  thread = (tile row, 16-channel half): 4 conflict-free LDS.128 of its own
+//                          row, A_lo = A - tf32(A) in registers, tcgen05.st of A and A_lo into a small
+//                          TMEM ring (64 columns per slot); afterwards the epilogue;
+//   warp 12     MMA        tcgen05.mma kind::tf32 with A from TMEM, B from shared memory.
+//
+// Why: with both operands in shared memory an M=128, N=128 tf32 MMA reads 8 KB per 64 cycles -- the
+// whole 128 B/clk of shared-memory bandwidth -- while cp.async, TMA and the splitter compete for the
+// same port (ncu: tensor pipe ~1/3 busy).  With A in TMEM the MMAs read only B (4 KB per 64 clk), the
+// A_lo tile is never written to shared memory, a stage shrinks from 2A+2B to A+2B (one more stage in
+// flight at N=128, two more at N=64) and the shared A tile is released as soon as it has been read.
+//
+// TMEM columns: [0, 64*TST) A ring (slot t: A at 64t, A_lo at 64t+32), then the correction
+// accumulator and NMAIN round-robin main accumulators of BN columns each.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int NLOADW2 = 4, NLOAD2 = NLOADW2 * 32;
+constexpr int NSPLITW2 = 8, NSPLIT2 = NSPLITW2 * 32;
+constexpr int NTHREADS2 = NLOAD2 + NSPLIT2 + 32;
+constexpr int MMA_WARP2 = NLOADW2 + NSPLITW2;
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int STAGE = A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = BN == 128 ? 4 : (BN == 64 ? 6 : 8);
+  static constexpr int TST = BN == 128 ? 2 : (BN == 64 ? 3 : 4);      // TMEM A-ring slots
+  static constexpr int ACC0 = TST * 64;                                 // first accumulator column
+  static constexpr int NACC = (512 - ACC0) / BN > 8 ? 8 : (512 - ACC0) / BN;
+  static constexpr int NMAIN = NACC - 1;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/;
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NTHREADS2, 1)
+conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + C::STAGES * C::STAGE;
+  auto landed_bar = [&](int s) { return bars + 8u * s; };                    // smem stage filled
+  auto sfree_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };       // smem stage reusable
+  auto tfull_bar = [&](int t) { return bars + 8u * (2 * C::STAGES + t); };   // TMEM slot written
+  auto tfree_bar = [&](int t) { return bars + 8u * (2 * C::STAGES + C::TST + t); };
+  const uint32_t acc_bar = bars + 8u * (2 * C::STAGES + 2 * C::TST);
+  const uint32_t tmem_slot = acc_bar + 8u;
+  auto a_smem = [&](int s) { return base + s * C::STAGE; };
+  auto b_raw = [&](int s) { return base + s * C::STAGE + A_TILE; };
+  auto b_lo = [&](int s) { return base + s * C::STAGE + A_TILE + C::B_TILE; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long m0 = (long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int nk = a.K / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed_bar(s), NLOAD2 + 1);    // cp.async completions + 1 expect_tx arrive
+      mbar_init(sfree_bar(s), NSPLIT2 + 1);    // every splitter has read A + the MMAs have read B
+    }
+    for (int t = 0; t < C::TST; ++t) {
+      mbar_init(tfull_bar(t), NSPLIT2);
+      mbar_init(tfree_bar(t), 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wlo) : "memory");
+  }
+  if (warp == MMA_WARP2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < NLOADW2) {
+    // ======================= loaders =======================
+    constexpr int RSTEP = NLOAD2 / 8;               // 16 rows per pass
+    constexpr int ROWS = BM / RSTEP;                // 8 rows per thread
+    const int j = tid & 7, rg = tid >> 3;
+    const float* rp[ROWS];
+    uint32_t vm[ROWS];
+    const int HoWo = a.Ho * a.Wo;
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      const int m = (int)m0 + rg + RSTEP * i;       // M < 2^31 (checked on the host)
+      rp[i] = a.x;
+      vm[i] = 0;
+      if (m < (int)a.M) {
+        int b = m / HoWo, r = m - b * HoWo;
+        int ho = r / a.Wo, wo = r - ho * a.Wo;
+        int hb, wb, hq, wq;
+        uint32_t mask = 0;
+        if (MODE == 0) {
+          hb = ho * a.stride - a.pad; wb = wo * a.stride - a.pad;
+          hq = hb; wq = wb;
+          for (int t = 0; t < a.KH; ++t) mask |= (uint32_t)(hb + t >= 0 && hb + t < a.Hg) << t;
+          for (int t = 0; t < a.KW; ++t) mask |= (uint32_t)(wb + t >= 0 && wb + t < a.Wg) << (8 + t);
+        } else {
+          hb = ho + a.pad; wb = wo + a.pad;
+          hq = hb / a.stride; wq = wb / a.stride;           // hb, wb >= 0
+          for (int t = 0; t < a.KH; ++t) {
+            int th = hb - t;
+            mask |= (uint32_t)(th >= 0 && th % a.stride == 0 && th / a.stride < a.Hg) << t;
+          }
+          for (int t = 0; t < a.KW; ++t) {
+            int tw = wb - t;
+            mask |= (uint32_t)(tw >= 0 && tw % a.stride == 0 && tw / a.stride < a.Wg) << (8 + t);
+          }
+        }
+        vm[i] = mask;
+        rp[i] = a.x + (((long)b * a.Hg + hq) * a.Wg + wq) * a.Cg + j * 4;
+      }
+    }
+    // rows rg + 16 i share (row & 7) == (rg & 7)
+    const uint32_t soff = (uint32_t)rg * 128u + (uint32_t)((j ^ (rg & 7)) << 4);
+    int kh = 0, kw = 0, c0 = 0;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % C::STAGES;
+      if (it >= C::STAGES) mbar_wait(sfree_bar(s), ((it / C::STAGES) - 1) & 1);
+      if (tid == 0) {
+        mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
+        tma_load_2d(b_raw(s), &tm_w, it * BK, n0, landed_bar(s));
+        tma_load_2d(b_lo(s), &tm_wlo, it * BK, n0, landed_bar(s));
+      }
+      const long toff = MODE == 0 ? ((long)kh * a.Wg + kw) * a.Cg + c0
+                                  : -((long)(kh / a.stride) * a.Wg + kw / a.stride) * a.Cg + c0;
+      const uint32_t dst = a_smem(s) + soff;
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        const bool ok = ((vm[i] >> kh) & (vm[i] >> (8 + kw)) & 1u) != 0;
+        cp_async16(dst + (uint32_t)i * RSTEP * 128u, ok ? rp[i] + toff : a.x, ok ? 16u : 0u);
+      }
+      cp_async_arrive_noinc(landed_bar(s));
+      c0 += BK;
+      if (c0 == a.Cg) { c0 = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
+    }
+  } else if (warp < MMA_WARP2) {
+    // ======================= splitters, then epilogue =======================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - NLOADW2) >> 2;       // which 16 of the 32 channels of a k-block
+    const int row = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % C::STAGES, t = kb % C::TST;
+      mbar_wait(landed_bar(s), (kb / C::STAGES) & 1);
+      uint32_t hi[16], lo[16];
+      const uint32_t ar = a_smem(s) + row_off;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint32_t chunk = (uint32_t)(half * 4 + jj);
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(hi[4 * jj]), "=r"(hi[4 * jj + 1]), "=r"(hi[4 * jj + 2]), "=r"(hi[4 * jj + 3])
+                     : "r"(ar + ((chunk ^ sw) << 4)));
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) lo[e] = __float_as_uint(lo_part(__uint_as_float(hi[e])));
+      // this thread's reads of the shared A tile are done (the operand ties the arrive to all four loads)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // %1" ::"r"(sfree_bar(s)),
+                   "r"(hi[0] ^ hi[4] ^ hi[8] ^ hi[12])
+                   : "memory");
+      if (kb >= C::TST) {
+        mbar_wait(tfree_bar(t), ((kb / C::TST) - 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t tcol = tlane + (uint32_t)(t * 64 + half * 16);
+      tmem_st16(tcol, hi);
+      tmem_st16(tcol + 32u, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(tfull_bar(t));
+    }
+    // ---- epilogue: warp (q, half) owns rows 32q..32q+31 and the 16-column chunks half, half+2, ... ----
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const long m = m0 + row;
+    const uint32_t trow = tlane + (uint32_t)C::ACC0;
+    const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
+#pragma unroll 1
+    for (int c = half * 16; c < BN; c += 32) {
+      // accumulators in summation order: main 0..nmain-1, then the (small) correction terms
+      float acc[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+      for (int g = 0; g <= nmain; g += 4) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = g + u;
+          if (i <= nmain) tmem_ld16_nowait(trow + (uint32_t)((i < nmain ? (1 + i) * BN : 0) + c), v[u]);
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (g + u <= nmain) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(v[u][e]);
+          }
+        }
+      }
+      if (m < a.M && n0 + c < a.N) {
+        float o[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float bv = a.bias ? a.bias[n0 + c + e] : 0.f;
+          o[e] = act_fn(acc[e] + bv, a.act);
+        }
+        float4* dst = reinterpret_cast<float4*>(a.y + m * a.N + n0 + c);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+      }
+    }
+  } else {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      const uint32_t d_corr = tmem_base + (uint32_t)C::ACC0;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % C::STAGES, t = kb % C::TST;
+        mbar_wait(tfull_bar(t), (kb / C::TST) & 1);
+        tc_fence_after();
+        const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
+        const uint32_t ta = tmem_base + (uint32_t)(t * 64), tal = ta + 32u;
+        const uint32_t d_main = d_corr + (uint32_t)((1 + kb % C::NMAIN) * BN);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);
+          umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+          umma_tf32_ts(d_corr, ta + 8u * k, dbl + adv, idesc, 1);
+          umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
+        }
+        umma_commit(sfree_bar(s));
+        umma_commit(tfree_bar(t));
+      }
+      umma_commit(acc_bar);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+template <int BN, int MODE>
+int launch_tc2(const TcArgs& a, cudaStream_t st) {
+  using C = Cfg2<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM);
+    if (e != cudaSuccess) {
+      fd::set_error("conv_tc2: cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  CUtensorMap tw, twl;
+  int rc = make_map_2d(&tw, a.w, a.N, a.K, BN);
+  if (rc) return rc;
+  rc = make_map_2d(&twl, a.wlo, a.N, a.K, BN);
+  if (rc) return rc;
+  dim3 grid(fd::cdiv(a.M, BM), fd::cdiv(a.N, BN));
+  conv_tc2_kernel<BN, MODE><<<grid, NTHREADS2, C::SMEM, st>>>(a, tw, twl);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int MODE>
+int dispatch_tc2(const TcArgs& a, cudaStream_t st) {
+  // Tile width: the widest BN dividing N, except that 128-wide layers with few pixel tiles run as
+  // 64-wide tiles (twice the CTAs for the 148 SMs, and four main accumulators instead of two).
+  FD_REQUIRE((((uintptr_t)a.w | (uintptr_t)a.wlo | (uintptr_t)a.x) & 15) == 0,
+             "conv_tc2: operands must be 16-byte aligned");
+  FD_REQUIRE(a.M < (1L << 31) && a.KH <= 8 && a.KW <= 8, "conv_tc2: problem too large (M=%ld, %dx%d)", a.M,
+             a.KH, a.KW);
+  static int narrow_below = -1;        // FD_TC2_NARROW: CTA-count threshold below which N=128 layers use N=64 tiles
+  if (narrow_below < 0) {
+    const char* e = getenv("FD_TC2_NARROW");
+    narrow_below = e ? atoi(e) : 64;
+  }
+  int bn = a.N % 128 == 0 ? 128 : (a.N % 64 == 0 ? 64 : (a.N % 32 == 0 ? 32 : 16));
+  if (bn == 128 && fd::cdiv(a.M, BM) * (a.N / 128) < narrow_below) bn = 64;
+  if (bn == 128) return launch_tc2<128, MODE>(a, st);
+  if (bn == 64) return launch_tc2<64, MODE>(a, st);
+  if (bn == 32) return launch_tc2<32, MODE>(a, st);
+  return launch_tc2<16, MODE>(a, st);
+}
+
+}  // namespace
+
+namespace fd {
+int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st) {
+  return mode == 0 ? dispatch_tc2<0>(a, st) : dispatch_tc2<1>(a, st);
+}
+}  // namespace fd

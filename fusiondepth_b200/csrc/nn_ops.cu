@@ -179,36 +179,50 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict_
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ ws, float* running_mean,
-                                   float* running_var, int training, float momentum, float eps,
-                                   float* save_mean, float* save_rstd, long M, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Per-channel batch statistics from the fp64 sums (training) or the running buffers (eval); the
+// running-statistic update and the saved mean / rstd are written once, by the first block row.
+struct BnStat { float mean, rstd; };
+__device__ __forceinline__ BnStat bn_channel_stat(const double* __restrict__ ws, float* running_mean,
+                                                  float* running_var, int training, float momentum, float eps,
+                                                  float* save_mean, float* save_rstd, long M, int C, int c,
+                                                  bool writer) {
+  BnStat r;
   if (training) {
     double mean = ws[c] / (double)M;
     double var = ws[C + c] / (double)M - mean * mean;
     if (var < 0) var = 0;
-    save_mean[c] = (float)mean;
-    save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-    double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
-    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + (double)momentum * mean);
-    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + (double)momentum * unb);
+    r.mean = (float)mean;
+    r.rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (writer) {
+      double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + (double)momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + (double)momentum * unb);
+    }
   } else {
-    save_mean[c] = running_mean[c];
-    save_rstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+    r.mean = running_mean[c];
+    r.rstd = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
   }
+  if (writer) { save_mean[c] = r.mean; save_rstd[c] = r.rstd; }
+  return r;
 }
 
+// pass 2 (finalize folded in): y = relu?((x - mean) * rstd * gamma + beta [+ residual])
 template <int VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const double* __restrict__ ws, float* running_mean, float* running_var,
+                                int training, float momentum, float eps, float* save_mean, float* save_rstd,
                                 int relu, float* __restrict__ y, long M, int C) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c >= C) return;
   float mu[VEC], rs[VEC], g[VEC], bt[VEC];
+  const bool writer = blockIdx.y == 0 && threadIdx.y == 0;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) { mu[i] = mean[c + i]; rs[i] = rstd[c + i]; g[i] = gamma[c + i]; bt[i] = beta[c + i]; }
+  for (int i = 0; i < VEC; ++i) {
+    BnStat st = bn_channel_stat(ws, running_mean, running_var, training, momentum, eps, save_mean, save_rstd, M,
+                                C, c + i, writer);
+    mu[i] = st.mean; rs[i] = st.rstd; g[i] = gamma[c + i]; bt[i] = beta[c + i];
+  }
   const long step = (long)gridDim.y * blockDim.y;
   for (long m = (long)blockIdx.y * blockDim.y + threadIdx.y; m < M; m += step) {
     float v[VEC], r[VEC];
@@ -574,13 +588,12 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
     else bn_stats_kernel<1><<<g.grid, g.block, sm, st>>>(x, ws, M, C);
     FD_CHECK_LAUNCH();
   }
-  bn_finalize_kernel<<<fd::cdiv(C, 128), 128, 0, st>>>(ws, running_mean, running_var, training,
-                                                       momentum, eps, save_mean, save_rstd, M, C);
-  FD_CHECK_LAUNCH();
   if (vec == 4)
-    bn_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, save_mean, save_rstd, relu, y, M, C);
+    bn_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, ws, running_mean, running_var,
+                                                   training, momentum, eps, save_mean, save_rstd, relu, y, M, C);
   else
-    bn_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, save_mean, save_rstd, relu, y, M, C);
+    bn_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, ws, running_mean, running_var,
+                                                   training, momentum, eps, save_mean, save_rstd, relu, y, M, C);
   FD_CHECK_LAUNCH();
   return 0;
 }

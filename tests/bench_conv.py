@@ -54,7 +54,7 @@ for B, Cin, H, W, Cout, k, s, p, name in SHAPES:
     gy = torch.randn(B, Cout, Ho, Wo, device="cuda").contiguous(memory_format=CL)
     flop = 2.0 * B * Ho * Wo * Cout * Cin * k * k
     row = "%-18s M=%6d N=%3d K=%4d " % (name, B * Ho * Wo, Cout, Cin * k * k)
-    for backend in ("tc", "cudacore"):
+    for backend in (("tc",) if os.environ.get("FD_BENCH_TC_ONLY") else ("tc", "cudacore")):
         ops.CONV_BACKEND = backend
         with torch.no_grad():
             tf = timeit(lambda: ops.conv2d(x, w, None, s, p, "none"))
