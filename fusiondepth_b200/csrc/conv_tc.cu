@@ -140,7 +140,7 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
     for (int it = 0; it < nk; ++it) {
       const int s = it % C::STAGES;
       if (it >= C::STAGES) mbar_wait(empty_bar(s), ((it / C::STAGES) - 1) & 1);
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
         tma_load_2d(b_raw(s), &tm_w, it * BK, n0, landed_bar(s));
         tma_load_2d(b_lo(s), &tm_wlo, it * BK, n0, landed_bar(s));
@@ -212,13 +212,13 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
     }
   } else {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % C::STAGES;
-        mbar_wait(full_bar(s), (kb / C::STAGES) & 1);
-        tc_fence_after();
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % C::STAGES;
+      mbar_wait(full_bar(s), (kb / C::STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t da = make_desc(a_raw(s)), dal = make_desc(a_lo(s));
         const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
         const uint32_t d_corr = tmem_base;
@@ -232,8 +232,9 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
         }
         umma_commit(empty_bar(s));
       }
-      umma_commit(acc_bar);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(acc_bar);
     __syncwarp();
   }
   tc_fence_before();
@@ -270,6 +271,7 @@ struct WgTcArgs {
   int M, K;
   int p_per_split;  // pixels per blockIdx.z (multiple of BP)
   int dbg;
+  int flags;        // bit 0: per-warp elected barrier arrivals + cp.async groups
 };
 
 // MN-major tf32 operands must use the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms: within a
@@ -321,8 +323,9 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(landed_bar(s), NLOAD + 1);
-      mbar_init(full_bar(s), NSPLIT);
+      // elected per-warp arrivals (flags bit 0): 32 lanes arriving on one mbarrier serialise
+      mbar_init(landed_bar(s), ((a.flags & 1) ? NLOADW : NLOAD) + 1);
+      mbar_init(full_bar(s), (a.flags & 1) ? NSPLIT / 32 : NSPLIT);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
@@ -356,11 +359,17 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
     }
     const int HoWo = a.Ho * a.Wo;
     const uint32_t soff = (uint32_t)rg * 128u + (uint32_t)((((j >> 1) ^ (rg & 3)) << 5) | ((j & 1) << 4));
+    const bool groups = (a.flags & 1) != 0;
     for (int it = 0; it < nst; ++it) {
       const int s = it % C::STAGES;
+      if (groups && it >= 2) {                   // the group issued two stages ago has landed
+        cp_async_wait<1>();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(landed_bar((it - 2) % C::STAGES));
+      }
       if (it >= C::STAGES) mbar_wait(empty_bar(s), ((it / C::STAGES) - 1) & 1);
       const int p0 = pbeg + it * BP;
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         mbar_expect_tx(landed_bar(s), C::B_BYTES);
 #pragma unroll
         for (int nb = 0; nb < C::NB; ++nb) tma_load_2d(b_raw(s) + nb * BLK, &tm_dy, n0 + 32 * nb, p0, landed_bar(s));
@@ -378,7 +387,14 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
         const float* src = ok ? a.x + (((long)b * a.H + h) * a.W + w) * a.Cin + cc[c] + j * 4 : a.x;
         cp_async16(dst + c * BLK, src, ok ? 16u : 0u);
       }
-      cp_async_arrive_noinc(landed_bar(s));
+      if (groups) cp_async_commit();
+      else cp_async_arrive_noinc(landed_bar(s));
+    }
+    if (groups) {
+      cp_async_wait<0>();
+      __syncwarp();
+      if (lane == 0)
+        for (int it = nst > 2 ? nst - 2 : 0; it < nst; ++it) mbar_arrive(landed_bar(it % C::STAGES));
     }
   } else if (warp < NLOADW + 4) {
     // ======================= splitters, then epilogue =======================
@@ -407,7 +423,12 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
                      : "memory");
       }
       fence_async_proxy();
-      mbar_arrive(full_bar(s));
+      if (a.flags & 1) {
+        __syncwarp();
+        if (elect_one()) mbar_arrive(full_bar(s));
+      } else {
+        mbar_arrive(full_bar(s));
+      }
     }
     const int ew = warp - NLOADW;
     mbar_wait(acc_bar, 0);
@@ -439,13 +460,14 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
     }
   } else {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int it = 0; it < nst; ++it) {
-        const int s = it % C::STAGES;
-        mbar_wait(full_bar(s), (it / C::STAGES) & 1);
-        tc_fence_after();
+    // converged warp, one elected lane issues (see elect_one in tc_common.cuh)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % C::STAGES;
+      mbar_wait(full_bar(s), (it / C::STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t da = make_desc_mn(a_raw(s), BLK), dal = make_desc_mn(a_lo(s), BLK);
         const uint64_t db = make_desc_mn(b_raw(s), BLK), dbl = make_desc_mn(b_lo(s), BLK);
         const uint32_t d_corr = tmem_base;
@@ -459,8 +481,9 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
         }
         umma_commit(empty_bar(s));
       }
-      umma_commit(acc_bar);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(acc_bar);
     __syncwarp();
   }
   tc_fence_before();
@@ -568,6 +591,14 @@ int launch_wgrad_tc(const WgTcArgs& a0, const float* dy, cudaStream_t st) {
 }  // namespace
 
 // FD_CONV_TC=v1 keeps both operands in shared memory (this file); default: A operand in TMEM (conv_tc2.cu)
+static int tc2_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FD_TC2_FLAGS");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 static bool tc_use_v2() {
   static int v = -1;
   if (v < 0) {
@@ -609,6 +640,7 @@ int fd_conv2d_fwd_tc(const float* x, const float* w, const float* w_lo, const fl
   a.N = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.act = act;
   a.M = (long)B * a.Ho * a.Wo;
   a.K = KH * KW * Cin;
+  a.flags = tc2_flags();
   if (tc_use_v2()) return fd::conv_tc2_dispatch(a, 0, (cudaStream_t)stream);
   return dispatch_tc<0>(a, (cudaStream_t)stream);
 }
@@ -627,6 +659,7 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
   a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.act = FD_ACT_NONE;
   a.M = (long)B * H * W;
   a.K = KH * KW * Cout;
+  a.flags = tc2_flags();
   if (tc_use_v2()) return fd::conv_tc2_dispatch(a, 1, (cudaStream_t)stream);
   return dispatch_tc<1>(a, (cudaStream_t)stream);
 }
@@ -647,6 +680,7 @@ int fd_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H,
   a.K = KH * KW * Cin;
   a.p_per_split = 0;
   a.dbg = getenv("FD_WGRAD_DEBUG") ? atoi(getenv("FD_WGRAD_DEBUG")) : 0;
+  a.flags = tc2_flags();
   FD_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "conv_wgrad_tc: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout % 128 == 0) return launch_wgrad_tc<128>(a, dy, st);

@@ -26,6 +26,16 @@ constexpr int NLOADW2 = 4, NLOAD2 = NLOADW2 * 32;
 constexpr int NSPLITW2 = 8, NSPLIT2 = NSPLITW2 * 32;
 constexpr int NTHREADS2 = NLOAD2 + NSPLIT2 + 32;
 constexpr int MMA_WARP2 = NLOADW2 + NSPLITW2;
+constexpr int LOOKAHEAD = 2;                     // cp.async groups a loader keeps in flight (< STAGES)
+
+// Timing experiment (FD_TC2_FLAGS bit 7): CTA (0,0) records clock64() at the hand-off points of one
+// thread per role into trace[role][k-block][4]; see tests/trace_conv.py.
+constexpr int TRACE_KB = 256;
+__device__ long long* g_trace = nullptr;
+#define FD_TRACE(role, kb, slot)                                                              \
+  do {                                                                                         \
+    if (tracing && (kb) < TRACE_KB) trace_buf[((role) * TRACE_KB + (kb)) * 4 + (slot)] = clock64(); \
+  } while (0)
 
 template <int BN>
 struct Cfg2 {
@@ -36,7 +46,7 @@ struct Cfg2 {
   static constexpr int ACC0 = TST * 64;                                 // first accumulator column
   static constexpr int NACC = (512 - ACC0) / BN > 8 ? 8 : (512 - ACC0) / BN;
   static constexpr int NMAIN = NACC - 1;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/ + 1536 /*row table*/;
 };
 
 template <int BN, int MODE>
@@ -60,14 +70,64 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   const long m0 = (long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int nk = a.K / BK;
+  long long* const trace_buf = (a.flags & 128) ? g_trace : nullptr;     // read once: stamps must stay cheap
+  const bool ktrace = trace_buf && blockIdx.x == 0 && blockIdx.y == 0;
+  if (ktrace && tid == NLOAD2) trace_buf[3 * TRACE_KB * 4 + 0] = clock64();
+
+  // Row table: tile row r -> (pointer to the first gathered channel of its pixel, valid-tap mask).
+  // One row per loader thread, published through shared memory by the prologue barrier -- not eight
+  // rows of integer divisions per thread in front of the first load (measured: 6.7k cycles per CTA).
+  const uint32_t tab_ptr = bars + 512u, tab_mask = tab_ptr + 8u * BM;
+  if (tid < BM) {
+    const long m = m0 + tid;
+    const float* ptr = a.x;
+    uint32_t mask = 0;
+    if (m < a.M) {
+      const uint32_t HoWo = (uint32_t)(a.Ho * a.Wo);
+      const uint32_t mu = (uint32_t)m;                       // M < 2^31 (checked on the host)
+      const uint32_t b = mu / HoWo, r = mu - b * HoWo;
+      const int ho = (int)(r / (uint32_t)a.Wo), wo = (int)(r - (uint32_t)ho * (uint32_t)a.Wo);
+      int hq, wq;
+      if (MODE == 0) {
+        const int hb = ho * a.stride - a.pad, wb = wo * a.stride - a.pad;
+        hq = hb; wq = wb;
+        for (int t = 0; t < a.KH; ++t) mask |= (uint32_t)(hb + t >= 0 && hb + t < a.Hg) << t;
+        for (int t = 0; t < a.KW; ++t) mask |= (uint32_t)(wb + t >= 0 && wb + t < a.Wg) << (8 + t);
+      } else {
+        const int hb = ho + a.pad, wb = wo + a.pad;          // >= 0
+        const int sh = a.stride == 1 ? 0 : (a.stride == 2 ? 1 : -1);
+        hq = sh >= 0 ? hb >> sh : hb / a.stride;
+        wq = sh >= 0 ? wb >> sh : wb / a.stride;
+        for (int t = 0; t < a.KH; ++t) {
+          const int th = hb - t;
+          const bool al = sh >= 0 ? (th & (a.stride - 1)) == 0 : th % a.stride == 0;
+          const int tq = sh >= 0 ? th >> sh : th / a.stride;
+          mask |= (uint32_t)(th >= 0 && al && tq < a.Hg) << t;
+        }
+        for (int t = 0; t < a.KW; ++t) {
+          const int tw = wb - t;
+          const bool al = sh >= 0 ? (tw & (a.stride - 1)) == 0 : tw % a.stride == 0;
+          const int tq = sh >= 0 ? tw >> sh : tw / a.stride;
+          mask |= (uint32_t)(tw >= 0 && al && tq < a.Wg) << (8 + t);
+        }
+      }
+      ptr = a.x + (((long)b * a.Hg + hq) * a.Wg + wq) * a.Cg;
+    }
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(tab_ptr + 8u * tid), "l"(ptr) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_mask + 4u * tid), "r"(mask) : "memory");
+  }
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(landed_bar(s), NLOAD2 + 1);    // cp.async completions + 1 expect_tx arrive
-      mbar_init(sfree_bar(s), NSPLIT2 + 1);    // every splitter has read A + the MMAs have read B
+      // One elected arrival per warp: 32 lanes arriving on the same mbarrier serialise, and with
+      // 256 arrivals per k-block that hand-off latency (not bandwidth) paced the whole pipeline.
+      // landed: 1 expect_tx arrive + either one arrival per loader warp (cp.async groups, flags bit 0)
+      // or one asynchronous cp.async.mbarrier arrival per loader thread
+      mbar_init(landed_bar(s), ((a.flags & 1) ? NLOADW2 : NLOAD2) + 1);
+      mbar_init(sfree_bar(s), NSPLITW2 + 1);   // every splitter warp has read A + the MMAs have read B
     }
     for (int t = 0; t < C::TST; ++t) {
-      mbar_init(tfull_bar(t), NSPLIT2);
+      mbar_init(tfull_bar(t), NSPLITW2);
       mbar_init(tfree_bar(t), 1);
     }
     mbar_init(acc_bar, 1);
@@ -85,6 +145,7 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (ktrace && tid == NLOAD2) g_trace[3 * TRACE_KB * 4 + 1] = clock64();
 
   if (warp < NLOADW2) {
     // ======================= loaders =======================
@@ -93,60 +154,60 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     const int j = tid & 7, rg = tid >> 3;
     const float* rp[ROWS];
     uint32_t vm[ROWS];
-    const int HoWo = a.Ho * a.Wo;
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
-      const int m = (int)m0 + rg + RSTEP * i;       // M < 2^31 (checked on the host)
-      rp[i] = a.x;
-      vm[i] = 0;
-      if (m < (int)a.M) {
-        int b = m / HoWo, r = m - b * HoWo;
-        int ho = r / a.Wo, wo = r - ho * a.Wo;
-        int hb, wb, hq, wq;
-        uint32_t mask = 0;
-        if (MODE == 0) {
-          hb = ho * a.stride - a.pad; wb = wo * a.stride - a.pad;
-          hq = hb; wq = wb;
-          for (int t = 0; t < a.KH; ++t) mask |= (uint32_t)(hb + t >= 0 && hb + t < a.Hg) << t;
-          for (int t = 0; t < a.KW; ++t) mask |= (uint32_t)(wb + t >= 0 && wb + t < a.Wg) << (8 + t);
-        } else {
-          hb = ho + a.pad; wb = wo + a.pad;
-          hq = hb / a.stride; wq = wb / a.stride;           // hb, wb >= 0
-          for (int t = 0; t < a.KH; ++t) {
-            int th = hb - t;
-            mask |= (uint32_t)(th >= 0 && th % a.stride == 0 && th / a.stride < a.Hg) << t;
-          }
-          for (int t = 0; t < a.KW; ++t) {
-            int tw = wb - t;
-            mask |= (uint32_t)(tw >= 0 && tw % a.stride == 0 && tw / a.stride < a.Wg) << (8 + t);
-          }
-        }
-        vm[i] = mask;
-        rp[i] = a.x + (((long)b * a.Hg + hq) * a.Wg + wq) * a.Cg + j * 4;
-      }
+      const uint32_t row = (uint32_t)(rg + RSTEP * i);
+      unsigned long long pv;
+      asm volatile("ld.shared.u64 %0, [%1];" : "=l"(pv) : "r"(tab_ptr + 8u * row));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vm[i]) : "r"(tab_mask + 4u * row));
+      rp[i] = reinterpret_cast<const float*>(pv) + j * 4;
     }
     // rows rg + 16 i share (row & 7) == (rg & 7)
     const uint32_t soff = (uint32_t)rg * 128u + (uint32_t)((j ^ (rg & 7)) << 4);
     int kh = 0, kw = 0, c0 = 0;
+    const bool groups = (a.flags & 1) != 0;
+    const bool tracing = trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
     for (int it = 0; it < nk; ++it) {
       const int s = it % C::STAGES;
+      FD_TRACE(0, it, 0);
+      if (groups && it >= LOOKAHEAD) {           // the group issued LOOKAHEAD k-blocks ago has landed
+        cp_async_wait<LOOKAHEAD - 1>();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(landed_bar((it - LOOKAHEAD) % C::STAGES));
+      }
+      FD_TRACE(0, it, 1);
       if (it >= C::STAGES) mbar_wait(sfree_bar(s), ((it / C::STAGES) - 1) & 1);
-      if (tid == 0) {
-        mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
-        tma_load_2d(b_raw(s), &tm_w, it * BK, n0, landed_bar(s));
-        tma_load_2d(b_lo(s), &tm_wlo, it * BK, n0, landed_bar(s));
+      FD_TRACE(0, it, 2);
+      if (warp == 0 && elect_one()) {
+        if (a.flags & 8) {                       // timing experiment: no loads at all
+          mbar_arrive(landed_bar(s));
+        } else {
+          mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
+          tma_load_2d(b_raw(s), &tm_w, it * BK, n0, landed_bar(s));
+          tma_load_2d(b_lo(s), &tm_wlo, it * BK, n0, landed_bar(s));
+        }
       }
       const long toff = MODE == 0 ? ((long)kh * a.Wg + kw) * a.Cg + c0
                                   : -((long)(kh / a.stride) * a.Wg + kw / a.stride) * a.Cg + c0;
       const uint32_t dst = a_smem(s) + soff;
+      if (!(a.flags & 8)) {
 #pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const bool ok = ((vm[i] >> kh) & (vm[i] >> (8 + kw)) & 1u) != 0;
-        cp_async16(dst + (uint32_t)i * RSTEP * 128u, ok ? rp[i] + toff : a.x, ok ? 16u : 0u);
+        for (int i = 0; i < ROWS; ++i) {
+          const bool ok = ((vm[i] >> kh) & (vm[i] >> (8 + kw)) & 1u) != 0;
+          cp_async16(dst + (uint32_t)i * RSTEP * 128u, ok ? rp[i] + toff : a.x, ok ? 16u : 0u);
+        }
       }
-      cp_async_arrive_noinc(landed_bar(s));
+      if (groups) cp_async_commit();
+      else cp_async_arrive_noinc(landed_bar(s));
+      FD_TRACE(0, it, 3);
       c0 += BK;
       if (c0 == a.Cg) { c0 = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
+    }
+    if (groups) {                                // drain: the last min(nk, LOOKAHEAD) groups
+      cp_async_wait<0>();
+      __syncwarp();
+      if (lane == 0)
+        for (int it = nk > LOOKAHEAD ? nk - LOOKAHEAD : 0; it < nk; ++it) mbar_arrive(landed_bar(it % C::STAGES));
     }
   } else if (warp < MMA_WARP2) {
     // ======================= splitters, then epilogue =======================
@@ -156,13 +217,18 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool tracing = trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && tid == NLOAD2;
     for (int kb = 0; kb < nk; ++kb) {
       const int s = kb % C::STAGES, t = kb % C::TST;
+      FD_TRACE(1, kb, 0);
       mbar_wait(landed_bar(s), (kb / C::STAGES) & 1);
+      FD_TRACE(1, kb, 1);
       uint32_t hi[16], lo[16];
       const uint32_t ar = a_smem(s) + row_off;
+      const bool skip_split = (a.flags & 4) != 0;      // timing experiment: hand-offs only
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
+        if (skip_split) { hi[4 * jj] = hi[4 * jj + 1] = hi[4 * jj + 2] = hi[4 * jj + 3] = 0u; continue; }
         const uint32_t chunk = (uint32_t)(half * 4 + jj);
         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(hi[4 * jj]), "=r"(hi[4 * jj + 1]), "=r"(hi[4 * jj + 2]), "=r"(hi[4 * jj + 3])
@@ -170,24 +236,29 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       }
 #pragma unroll
       for (int e = 0; e < 16; ++e) lo[e] = __float_as_uint(lo_part(__uint_as_float(hi[e])));
-      // this thread's reads of the shared A tile are done (the operand ties the arrive to all four loads)
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // %1" ::"r"(sfree_bar(s)),
-                   "r"(hi[0] ^ hi[4] ^ hi[8] ^ hi[12])
-                   : "memory");
+      // the warp is converged: once the low parts are computed every lane's loads have returned
+      __syncwarp();
+      if (elect_one()) mbar_arrive(sfree_bar(s));
       if (kb >= C::TST) {
         mbar_wait(tfree_bar(t), ((kb / C::TST) - 1) & 1);
         tc_fence_after();
       }
+      FD_TRACE(1, kb, 2);
       const uint32_t tcol = tlane + (uint32_t)(t * 64 + half * 16);
-      tmem_st16(tcol, hi);
-      tmem_st16(tcol + 32u, lo);
-      tmem_wait_st();
+      if (!skip_split) {
+        tmem_st16(tcol, hi);
+        tmem_st16(tcol + 32u, lo);
+        tmem_wait_st();
+      }
       tc_fence_before();
-      mbar_arrive(tfull_bar(t));
+      __syncwarp();
+      if (elect_one()) mbar_arrive(tfull_bar(t));
+      FD_TRACE(1, kb, 3);
     }
     // ---- epilogue: warp (q, half) owns rows 32q..32q+31 and the 16-column chunks half, half+2, ... ----
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    if (ktrace && tid == NLOAD2) g_trace[3 * TRACE_KB * 4 + 2] = clock64();
     const long m = m0 + row;
     const uint32_t trow = tlane + (uint32_t)C::ACC0;
     const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
@@ -227,33 +298,51 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     }
   } else {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
-      const uint32_t d_corr = tmem_base + (uint32_t)C::ACC0;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % C::STAGES, t = kb % C::TST;
-        mbar_wait(tfull_bar(t), (kb / C::TST) & 1);
-        tc_fence_after();
+    // The whole warp walks the loop and waits on the barriers (converged); one lane issues.  A lone
+    // lane looping while 31 lanes sit at a convergence barrier paid for it in hand-off latency.
+    const bool plain = (a.flags & 64) != 0 && (a.flags & 16) != 0;   // experiment: arrive without commit
+    const bool tracing = trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    const uint32_t d_corr = tmem_base + (uint32_t)C::ACC0;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % C::STAGES, t = kb % C::TST;
+      FD_TRACE(2, kb, 0);
+      mbar_wait(tfull_bar(t), (kb / C::TST) & 1);
+      FD_TRACE(2, kb, 1);
+      tc_fence_after();
+      FD_TRACE(2, kb, 2);
+      if (elect_one()) {
         const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
         const uint32_t ta = tmem_base + (uint32_t)(t * 64), tal = ta + 32u;
         const uint32_t d_main = d_corr + (uint32_t)((1 + kb % C::NMAIN) * BN);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);
-          umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
-          umma_tf32_ts(d_corr, ta + 8u * k, dbl + adv, idesc, 1);
-          umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
+          if (!(a.flags & (2 | 16))) {
+            umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+            umma_tf32_ts(d_corr, ta + 8u * k, dbl + adv, idesc, 1);
+          }
+          if (!(a.flags & 16)) umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
         }
-        umma_commit(sfree_bar(s));
-        umma_commit(tfree_bar(t));
+        if (plain) {
+          mbar_arrive(sfree_bar(s));
+          mbar_arrive(tfree_bar(t));
+        } else {
+          umma_commit(sfree_bar(s));
+          umma_commit(tfree_bar(t));
+        }
       }
-      umma_commit(acc_bar);
+      __syncwarp();
+      FD_TRACE(2, kb, 3);
     }
+    if (elect_one()) umma_commit(acc_bar);
     __syncwarp();
   }
+  if (ktrace && tid == NLOAD2) g_trace[3 * TRACE_KB * 4 + 3] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (ktrace && tid == NLOAD2) g_trace[3 * TRACE_KB * 4 + 4] = clock64();
   if (warp == MMA_WARP2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
@@ -306,6 +395,12 @@ int dispatch_tc2(const TcArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+extern "C" int fd_debug_set_conv_trace(void* device_buffer) {
+  // device_buffer: (3 * 256 * 4 + 8) int64 slots, or NULL to switch tracing off
+  cudaError_t e = cudaMemcpyToSymbol(g_trace, &device_buffer, sizeof(void*));
+  return e == cudaSuccess ? 0 : 1;
+}
 
 namespace fd {
 int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st) {

@@ -184,8 +184,8 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict_
 struct BnStat { float mean, rstd; };
 __device__ __forceinline__ BnStat bn_channel_stat(const double* __restrict__ ws, float* running_mean,
                                                   float* running_var, int training, float momentum, float eps,
-                                                  float* save_mean, float* save_rstd, long M, int C, int c,
-                                                  bool writer) {
+                                                  float stat_weight, float* save_mean, float* save_rstd,
+                                                  long M, int C, int c, bool writer) {
   BnStat r;
   if (training) {
     double mean = ws[c] / (double)M;
@@ -195,8 +195,15 @@ __device__ __forceinline__ BnStat bn_channel_stat(const double* __restrict__ ws,
     r.rstd = (float)(1.0 / sqrt(var + (double)eps));
     if (writer) {
       double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
-      running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + (double)momentum * mean);
-      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + (double)momentum * unb);
+      if (stat_weight >= 0.f) {
+        // order-free form for calls that run concurrently (other micro-batch / other stream): the
+        // caller pre-decays the buffer once per step and every call adds its weighted statistic
+        atomicAdd(&running_mean[c], (float)((double)stat_weight * mean));
+        atomicAdd(&running_var[c], (float)((double)stat_weight * unb));
+      } else {
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + (double)momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + (double)momentum * unb);
+      }
     }
   } else {
     r.mean = running_mean[c];
@@ -211,16 +218,16 @@ template <int VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const double* __restrict__ ws, float* running_mean, float* running_var,
-                                int training, float momentum, float eps, float* save_mean, float* save_rstd,
-                                int relu, float* __restrict__ y, long M, int C) {
+                                int training, float momentum, float eps, float stat_weight, float* save_mean,
+                                float* save_rstd, int relu, float* __restrict__ y, long M, int C) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c >= C) return;
   float mu[VEC], rs[VEC], g[VEC], bt[VEC];
   const bool writer = blockIdx.y == 0 && threadIdx.y == 0;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    BnStat st = bn_channel_stat(ws, running_mean, running_var, training, momentum, eps, save_mean, save_rstd, M,
-                                C, c + i, writer);
+    BnStat st = bn_channel_stat(ws, running_mean, running_var, training, momentum, eps, stat_weight, save_mean,
+                                save_rstd, M, C, c + i, writer);
     mu[i] = st.mean; rs[i] = st.rstd; g[i] = gamma[c + i]; bt[i] = beta[c + i];
   }
   const long step = (long)gridDim.y * blockDim.y;
@@ -577,7 +584,7 @@ int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long 
 int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
               float* running_mean, float* running_var, int training, float momentum, float eps,
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
-              void* stream) {
+              float stat_weight, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int vec = (C % 4 == 0) ? 4 : 1;
   BnGeom g = bn_geom(M, C, vec);
@@ -590,10 +597,12 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
   }
   if (vec == 4)
     bn_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, ws, running_mean, running_var,
-                                                   training, momentum, eps, save_mean, save_rstd, relu, y, M, C);
+                                                   training, momentum, eps, stat_weight, save_mean, save_rstd, relu, y,
+                                                   M, C);
   else
     bn_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, residual, gamma, beta, ws, running_mean, running_var,
-                                                   training, momentum, eps, save_mean, save_rstd, relu, y, M, C);
+                                                   training, momentum, eps, stat_weight, save_mean, save_rstd, relu, y,
+                                                   M, C);
   FD_CHECK_LAUNCH();
   return 0;
 }

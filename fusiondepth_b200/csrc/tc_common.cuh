@@ -17,6 +17,7 @@ struct TcArgs {
   int B, Hg, Wg, Cg, Ho, Wo, N, KH, KW, stride, pad, act;
   long M;
   int K;
+  int flags;          // conv_tc2: bit 0 = loader signals `landed` per warp through cp.async groups
 };
 // conv_tc2.cu: A-operand-in-TMEM kernels (mode 0 forward, 1 data gradient)
 int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st);
@@ -126,6 +127,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&o)[16]) {
 }
 __device__ __forceinline__ float lo_part(float v) {
   return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+}
+
+// One lane of a converged warp.  Unlike `lane == 0`, ptxas knows that code guarded by elect.sync runs
+// on exactly one thread, so warp-uniform instructions (UTCHMMA, UTMALDG, UTCBAR, barrier arrives on
+// uniform addresses) are issued straight from the uniform datapath instead of through a per-thread
+// election loop around every instruction (measured: ~100 cycles per tcgen05.mma issued).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // A operand from tensor memory (lane = tile row, one 32-bit column per K element), B from shared memory

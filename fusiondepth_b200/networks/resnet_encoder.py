@@ -35,10 +35,15 @@ class BatchNorm2d(nn.BatchNorm2d):
 
     def forward(self, x, residual=None, relu=False):
         training = self.training or not self.track_running_stats
+        stat_weight = -1.0
         if self.training and self.track_running_stats:
-            self.num_batches_tracked += 1
+            sched = ops.BN_SCHEDULE
+            if sched is not None and self.momentum is not None:
+                stat_weight = sched.next_weight(self)      # the step bumps num_batches_tracked itself
+            if stat_weight < 0:
+                self.num_batches_tracked += 1
         return ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var,
-                              residual, training, self.momentum, self.eps, relu)
+                              residual, training, self.momentum, self.eps, relu, stat_weight)
 
 
 class _Downsample(nn.Sequential):

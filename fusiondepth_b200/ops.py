@@ -54,6 +54,51 @@ def _cached(key, make):
 CL = torch.channels_last
 
 
+class BNSchedule:
+    """Order-free BatchNorm running-statistic updates for one optimiser step.
+
+    nn.BatchNorm2d applies r <- (1-m) r + m s once per call, in call order.  TrainStep runs the
+    micro-batches (and the two pose-pair calls of a trunk) concurrently on different streams, so it
+    uses the closed form instead: n calls give r <- (1-m)^n r + sum_k m (1-m)^(n-1-k) s_k.
+    begin_step() decays every buffer once (and bumps num_batches_tracked by n); call k of a layer
+    then adds its weighted statistic atomically (fd_bn_fwd stat_weight >= 0)."""
+
+    def __init__(self, calls_per_step: Dict):
+        self.n = dict(calls_per_step)               # BatchNorm2d module -> calls per optimiser step
+        self.count: Dict = {}
+        groups: Dict = {}
+        for mod, n in self.n.items():
+            groups.setdefault((float(mod.momentum), int(n)), []).append(mod)
+        self.groups = [((1.0 - m) ** n, n, [b for mod in mods for b in (mod.running_mean, mod.running_var)],
+                        [mod.num_batches_tracked for mod in mods]) for (m, n), mods in groups.items()]
+
+    def begin_step(self):
+        self.count = {}
+        for decay, n, bufs, nbt in self.groups:
+            torch._foreach_mul_(bufs, decay)
+            torch._foreach_add_(nbt, n)
+
+    def next_weight(self, mod) -> float:
+        n = self.n.get(mod)
+        if n is None:
+            return -1.0
+        k = self.count.get(mod, 0)
+        if k >= n:
+            raise RuntimeError("BNSchedule: BatchNorm layer called %d times in one step, scheduled for %d" % (k + 1, n))
+        self.count[mod] = k + 1
+        m = float(mod.momentum)
+        return m * (1.0 - m) ** (n - 1 - k)
+
+    def end_step(self):
+        bad = [(self.count.get(mod, 0), n) for mod, n in self.n.items() if self.count.get(mod, 0) != n]
+        if bad:
+            raise RuntimeError("BNSchedule: %d BatchNorm layers were not called as scheduled, e.g. %s" % (len(bad), bad[0]))
+
+
+# Set by training.TrainStep while a step is being issued; None => nn.BatchNorm2d's in-place update.
+BN_SCHEDULE: Optional[BNSchedule] = None
+
+
 # Optional per-kernel-family timing (bench.py's roofline leg): when PROFILE is a dict, every
 # timed call appends (start_event, end_event, algorithmic_work) under its family name.  Events are
 # recorded on the launching stream; nothing is synchronised here.
@@ -143,7 +188,13 @@ class Conv2dFn(torch.autograd.Function):
         Wo = (W + 2 * pad - KW) // stride + 1
         y = empty_nhwc(B, Cout, Ho, Wo, x.device)
         use_tc = CONV_BACKEND == "tc" and Cin % 32 == 0 and Cout % 16 == 0
-        if use_tc:
+        ctx.cout1 = bool(lib.fd_conv2d_cout1_supported(Cin, Cout, KH, KW, stride)) and CONV_BACKEND != "cudacore"
+        if ctx.cout1:
+            # disparity heads: one output channel, streaming kernels (conv_small.cu)
+            with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
+                _lib.check(lib.fd_conv2d_cout1_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, pad, act,
+                                                   _stream()), "fd_conv2d_cout1_fwd")
+        elif use_tc:
             def make_lo():
                 t = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
                 _lib.check(lib.fd_tf32_split(_p(w), _p(t), w.numel(), _stream()), "fd_tf32_split")
@@ -181,8 +232,22 @@ class Conv2dFn(torch.autograd.Function):
                                       act, st), "fd_act_bwd")
             dy = dpre
         dx = None
+        if ctx.cout1:
+            if ctx.needs_input_grad[0]:
+                dx = empty_nhwc(B, Cin, H, W, x.device)
+                with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
+                    _lib.check(lib.fd_conv2d_cout1_dgrad(_p(dy), _p(w), _p(dx), B, H, W, Cin, pad, st),
+                               "fd_conv2d_cout1_dgrad")
+            dw = None
+            if ctx.needs_input_grad[1]:
+                dw = ctx.wg if ctx.wg is not None else torch.empty(
+                    (Cout, Cin, KH, KW), device=x.device, dtype=torch.float32, memory_format=CL).zero_()
+                with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
+                    _lib.check(lib.fd_conv2d_cout1_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, pad, st),
+                               "fd_conv2d_cout1_wgrad")
+            return (dx, None if ctx.wg is not None else dw, None if ctx.bg is not None else dbias,
+                    None, None, None)
         if ctx.needs_input_grad[0]:
-            wt = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
             dx = empty_nhwc(B, Cin, H, W, x.device)
             if CONV_BACKEND == "tc" and Cout % 32 == 0 and Cin % 16 == 0:
                 def make_t():
@@ -196,6 +261,7 @@ class Conv2dFn(torch.autograd.Function):
                     _lib.check(lib.fd_conv2d_dgrad_tc(_p(dy), _p(wt), _p(wtlo), _p(dx), B, H, W, Cin,
                                                       Cout, KH, KW, stride, pad, st), "fd_conv2d_dgrad_tc")
             else:
+                wt = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
                 _lib.check(lib.fd_weight_transpose(_p(w), _p(wt), Cout, KH * KW, Cin, st),
                            "fd_weight_transpose")
                 with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
@@ -292,7 +358,7 @@ def stem_conv(x, weight):
 class BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps,
-                relu):
+                relu, stat_weight):
         _require_cuda(x, "batch_norm")
         lib = _lib.load()
         x = nhwc(x)
@@ -306,7 +372,7 @@ class BatchNormFn(torch.autograd.Function):
         ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
         _lib.check(lib.fd_bn_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(running_mean),
                                  _p(running_var), int(training), momentum, eps, int(relu), _p(y),
-                                 _p(mean), _p(rstd), _p(ws), M, C, _stream()), "fd_bn_fwd")
+                                 _p(mean), _p(rstd), _p(ws), M, C, stat_weight, _stream()), "fd_bn_fwd")
         ctx.save_for_backward(x, y, gamma, mean, rstd)
         ctx.cfg = (int(relu), int(training), residual is not None)
         ctx.gg, ctx.gb = _direct_grad(gamma), _direct_grad(beta)
@@ -330,14 +396,14 @@ class BatchNormFn(torch.autograd.Function):
                                  _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, int(direct),
                                  _stream()), "fd_bn_bwd")
         if direct:
-            return dx, None, None, None, None, dres, None, None, None, None
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+            return dx, None, None, None, None, dres, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 
 def batch_norm(x, gamma, beta, running_mean, running_var, residual=None, training=True,
-               momentum=0.1, eps=1e-5, relu=False):
+               momentum=0.1, eps=1e-5, relu=False, stat_weight=-1.0):
     return BatchNormFn.apply(x, gamma, beta, running_mean, running_var, residual, bool(training),
-                             float(momentum), float(eps), bool(relu))
+                             float(momentum), float(eps), bool(relu), float(stat_weight))
 
 
 # --------------------------------------------------------------------------------------------

@@ -244,7 +244,7 @@ class TrainStep:
 
     def __init__(self, models, lr: float = 1e-4, accumulate: int = 1, opts: Optional[Dict] = None,
                  process_group=None, parallel_trunks: bool = True, direct_grad: bool = True,
-                 cache_weight_prep: bool = True):
+                 cache_weight_prep: bool = True, concurrent_microbatches: bool = True):
         self.models = models
         self.accumulate = accumulate
         self.lr = float(lr)
@@ -259,7 +259,16 @@ class TrainStep:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.direct_grad, self.cache_weight_prep = direct_grad, cache_weight_prep
-        self.streams = TrunkStreams(dev) if parallel_trunks else None
+        # The micro-batches of a step are independent given the weights (gradients accumulate with
+        # atomics, BatchNorm running statistics through ops.BNSchedule), so each gets its own stream
+        # and trunk streams: while one micro-batch walks its serial decoder -> loss -> decoder
+        # backward chain, the other one's trunks keep the SMs busy.
+        self.concurrent = bool(concurrent_microbatches) and accumulate > 1
+        nsets = accumulate if self.concurrent else 1
+        self.trunks = [TrunkStreams(dev) if parallel_trunks else None for _ in range(nsets)]
+        self.mb_streams = [torch.cuda.Stream(device=dev) for _ in range(nsets)] if self.concurrent else []
+        self.streams = self.trunks[0]
+        self.bn_schedule = self._make_bn_schedule() if self.concurrent or parallel_trunks else None
         self.stream = torch.cuda.Stream(device=dev)      # warm-up and capture share one stream
         self.graph = None
         self.static_inputs = None
@@ -268,28 +277,64 @@ class TrainStep:
         for m in models.values():
             m.train()
 
+    def _make_bn_schedule(self):
+        """Calls per optimiser step of every BatchNorm layer: the pose trunks see both image pairs
+        of a micro-batch (trainer.py:339-365), every other trunk one batch."""
+        from .networks.resnet_encoder import BatchNorm2d
+        calls = {}
+        for name, m in self.models.items():
+            per_mb = 2 if name in ("pose_encoder", "beam_encoder_pose") else 1
+            for mod in m.modules():
+                if isinstance(mod, BatchNorm2d) and mod.track_running_stats and mod.momentum is not None:
+                    calls[mod] = per_mb * self.accumulate
+        return ops.BNSchedule(calls)
+
     # -- eager -------------------------------------------------------------------------------
     def _run(self, batches: Sequence[Dict], noises: Sequence[Dict]):
         self.flat.zero_grad()
         ops.DIRECT_GRAD = self.direct_grad
         ops.WEIGHT_CACHE = {} if self.cache_weight_prep else None
+        ops.BN_SCHEDULE = self.bn_schedule
         try:
-            return self._run_inner(batches, noises)
+            if self.bn_schedule is not None:
+                self.bn_schedule.begin_step()
+            out = self._run_inner(batches, noises)
+            if self.bn_schedule is not None:
+                self.bn_schedule.end_step()
+            return out
         finally:
             ops.DIRECT_GRAD = False
             ops.WEIGHT_CACHE = None
+            ops.BN_SCHEDULE = None
+
+    def _micro_batch(self, inputs, noise, trunks):
+        _, losses = process_batch(self.models, inputs, noise, self.opts, streams=trunks)
+        loss = losses["loss"] / self.accumulate
+        loss.backward()
+        if trunks is not None:
+            # direct gradient accumulation bypasses AccumulateGrad, so autograd has no leaf
+            # streams to join: wait for every trunk stream's backward kernels explicitly
+            trunks.join(range(len(trunks.side)))
+        return loss.detach()
 
     def _run_inner(self, batches: Sequence[Dict], noises: Sequence[Dict]):
         total = None
-        for inputs, noise in zip(batches, noises):
-            _, losses = process_batch(self.models, inputs, noise, self.opts, streams=self.streams)
-            loss = losses["loss"] / self.accumulate
-            loss.backward()
-            if self.streams is not None:
-                # direct gradient accumulation bypasses AccumulateGrad, so autograd has no leaf
-                # streams to join: wait for every trunk stream's backward kernels explicitly
-                self.streams.join(range(len(self.streams.side)))
-            total = loss.detach() if total is None else total + loss.detach()
+        if self.concurrent:
+            cur = torch.cuda.current_stream()
+            parts = []
+            for i, (inputs, noise) in enumerate(zip(batches, noises)):
+                ms = self.mb_streams[i]
+                ms.wait_stream(cur)
+                with torch.cuda.stream(ms):
+                    parts.append(self._micro_batch(inputs, noise, self.trunks[i]))
+            for ms in self.mb_streams:
+                cur.wait_stream(ms)
+            for part in parts:
+                total = part if total is None else total + part
+        else:
+            for inputs, noise in zip(batches, noises):
+                part = self._micro_batch(inputs, noise, self.trunks[0])
+                total = part if total is None else total + part
         reduce_gradients(self.flat, self.world, self.pg)
         ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.adam_state,
                       self.lr, grad_scale=1.0 / self.world)

@@ -141,6 +141,19 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
  * zero-initialised or hold an accumulator. */
 int fd_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin,
                        int Cout, int KH, int KW, int stride, int pad, void* stream);
+/* Single-output-channel 3x3 stride-1 convolutions (the disparity heads, reference
+ * networks/depth_decoder.py:52-58 + layers.py:115-130) as streaming kernels: x [B,H,W,Cin] NHWC,
+ * w [1,3,3,Cin], y / dy [B,Ho,Wo] with Ho = H + 2*pad - 2.  wgrad ADDS into dw (atomics). */
+int fd_conv2d_cout1_supported(int Cin, int Cout, int KH, int KW, int stride);
+int fd_conv2d_cout1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                        int Cin, int pad, int act, void* stream);
+int fd_conv2d_cout1_dgrad(const float* dy, const float* w, float* dx, int B, int H, int W, int Cin, int pad,
+                          void* stream);
+int fd_conv2d_cout1_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int pad,
+                          void* stream);
+/* Profiling aid: with FD_TC2_FLAGS bit 7 set, CTA (0,0) of the tensor-core conv kernels writes
+ * clock64() stamps of its pipeline roles into this device buffer ((3*256*4 + 8) int64); NULL = off. */
+int fd_debug_set_conv_trace(void* device_buffer);
 /* dpre = dy * act'(.) computed from the activation output y; dbias[c] += sum_m dpre[m,c] */
 int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long M, int C, int act,
                void* stream);
@@ -148,11 +161,14 @@ int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long 
 /* BatchNorm2d (+ optional residual add, + optional ReLU) over M = B*H*W rows of C channels.
  * training: batch statistics, running stats updated (momentum, unbiased var).
  * ws: 2*C doubles of scratch.  save_mean/save_rstd [C] are outputs used by the backward.
+ * stat_weight < 0: running = (1-momentum)*running + momentum*stat (nn.BatchNorm2d).  stat_weight >= 0:
+ * running += stat_weight*stat with atomics -- for calls of one layer that run concurrently inside an
+ * optimiser step, after the caller has decayed the buffers by (1-momentum)^n_calls once.
  * accumulate_param_grads: dgamma/dbeta are added (atomically) into existing buffers instead of set. */
 int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
               float* running_mean, float* running_var, int training, float momentum, float eps,
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
-              void* stream);
+              float stat_weight, void* stream);
 int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
               const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
               float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,

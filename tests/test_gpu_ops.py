@@ -217,3 +217,30 @@ def test_stem_conv(cuda, C):
     assert rel_err(y.detach().cpu(), ref.detach()) < 5e-6
     assert rel_err(wc.grad.cpu(), wr.grad) < 2e-5
     assert wc.grad.is_contiguous(memory_format=CL)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 34, 50, 0, "sigmoid"), (2, 128, 10, 22, 0, "sigmoid"),
+                                  (1, 64, 13, 17, 1, "tanh"), (3, 32, 8, 8, 1, "none")])
+def test_conv_single_output_channel(cuda, case):
+    """disparity heads (Conv3x3 -> 1 channel, depth_decoder.py:52-58): streaming cout1 kernels vs fp64"""
+    from fusiondepth_b200 import ops, _lib
+    B, Cin, H, W, pad, act = case
+    assert _lib.load().fd_conv2d_cout1_supported(Cin, 1, 3, 3, 1)
+    x = _rand((B, Cin, H, W), 21)
+    w = _rand((1, Cin, 3, 3), 22, (1.0 / (Cin * 9)) ** 0.5)
+    b = _rand((1,), 23, 0.1)
+    fn = {"sigmoid": torch.sigmoid, "tanh": torch.tanh, "none": lambda t: t}[act]
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = fn(F.conv2d(xr, wr, br, 1, pad))
+    gy = _rand(tuple(ref.shape), 24)
+    ref.backward(gy.double())
+    xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    wc = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    bc = b.cuda().requires_grad_(True)
+    yc = ops.conv2d(xc, wc, bc, 1, pad, act)
+    yc.backward(gy.cuda())
+    assert yc.shape == ref.shape
+    assert rel_err(yc.detach().cpu(), ref.detach()) < 2e-6
+    assert rel_err(xc.grad.cpu(), xr.grad) < 2e-6
+    assert rel_err(wc.grad.cpu(), wr.grad) < 1e-5
+    assert rel_err(bc.grad.cpu(), br.grad) < 1e-5

@@ -117,6 +117,18 @@ def test_train_step_vs_oracle_and_adam(cuda):
     loss = step.step(cb, cn)
     torch.cuda.synchronize()
     assert abs(float(loss) - tot) < 1e-4 * abs(tot)
+    # BatchNorm running statistics: the step's order-free update (concurrent micro-batches, both
+    # pose pairs of a trunk) must equal the oracle's sequential nn.BatchNorm2d updates
+    nbuf = 0
+    for name in models:
+        for k, b in models[name].named_buffers():
+            ref = osd[name][k]
+            if k.endswith("num_batches_tracked"):
+                assert int(b) == int(ref), (name, k, int(b), int(ref))
+            else:
+                assert rel_err(b.cpu(), ref) < 1e-5, (name, k)
+            nbuf += 1
+    assert nbuf >= 200
     # compare the gradient of a few tensors and the Adam-updated weights
     for name, key in (("depth", "decoder.0.conv.conv.weight"), ("pose", "net.3.weight"),
                       ("encoder", "encoder.layer1.0.conv1.weight"), ("beam_encoder_pose", "encoder.conv1.weight")):
