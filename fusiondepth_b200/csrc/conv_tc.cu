@@ -298,8 +298,14 @@ struct WgCfg {
   static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
 };
 
+// Roles (576 threads): warps 0-7 input-pixel gather (cp.async), 8-15 splitters then epilogue, 16 MMA
+// issue, 17 dY tiles by TMA.
+constexpr int WG_NSPLITW = 8, WG_NSPLIT = WG_NSPLITW * 32;
+constexpr int WG_MMA_WARP = NLOADW + WG_NSPLITW, WG_TMA_WARP = WG_MMA_WARP + 1;
+constexpr int WG_NTHREADS = NLOAD + WG_NSPLIT + 64;
+
 template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(WG_NTHREADS, 1)
 conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
   using C = WgCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -325,14 +331,14 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
     for (int s = 0; s < C::STAGES; ++s) {
       // elected per-warp arrivals (flags bit 0): 32 lanes arriving on one mbarrier serialise
       mbar_init(landed_bar(s), ((a.flags & 1) ? NLOADW : NLOAD) + 1);
-      mbar_init(full_bar(s), (a.flags & 1) ? NSPLIT / 32 : NSPLIT);
+      mbar_init(full_bar(s), (a.flags & 1) ? WG_NSPLITW : WG_NSPLIT);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dy) : "memory");
   }
-  if (warp == NLOADW + 4) {
+  if (warp == WG_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "n"(C::TMEM_COLS)
                  : "memory");
@@ -357,9 +363,22 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
       cc[c] = k - tap * a.Cin;
       kh[c] = tap / a.KW; kw[c] = tap - kh[c] * a.KW;
     }
-    const int HoWo = a.Ho * a.Wo;
     const uint32_t soff = (uint32_t)rg * 128u + (uint32_t)((((j >> 1) ^ (rg & 3)) << 5) | ((j & 1) << 4));
     const bool groups = (a.flags & 1) != 0;
+    // this thread's pixel (pbeg + rg, then +32 per stage) as (b, ho, wo), advanced without divisions;
+    // 32-bit element offsets (host: |x| < 2^31 elements)
+    int pb = 0, pho = 0, pwo = 0;
+    {
+      const int p = pbeg + rg;
+      const int HoWo = a.Ho * a.Wo;
+      pb = p / HoWo;
+      const int r = p - pb * HoWo;
+      pho = r / a.Wo;
+      pwo = r - pho * a.Wo;
+    }
+    int tapoff[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tapoff[c] = (kh[c] * a.W + kw[c]) * a.Cin + cc[c] + j * 4;
     for (int it = 0; it < nst; ++it) {
       const int s = it % C::STAGES;
       if (groups && it >= 2) {                   // the group issued two stages ago has landed
@@ -368,25 +387,18 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
         if (elect_one()) mbar_arrive(landed_bar((it - 2) % C::STAGES));
       }
       if (it >= C::STAGES) mbar_wait(empty_bar(s), ((it / C::STAGES) - 1) & 1);
-      const int p0 = pbeg + it * BP;
-      if (warp == 0 && elect_one()) {
-        mbar_expect_tx(landed_bar(s), C::B_BYTES);
-#pragma unroll
-        for (int nb = 0; nb < C::NB; ++nb) tma_load_2d(b_raw(s) + nb * BLK, &tm_dy, n0 + 32 * nb, p0, landed_bar(s));
-      }
-      const int p = p0 + rg;
-      const bool pok = p < pend;
-      int b = 0, ho = 0, wo = 0;
-      if (pok) { b = p / HoWo; int r = p - b * HoWo; ho = r / a.Wo; wo = r - ho * a.Wo; }
-      const int hb = ho * a.stride - a.pad, wb = wo * a.stride - a.pad;
+      const bool pok = pbeg + it * BP + rg < pend;
+      const int hb = pho * a.stride - a.pad, wb = pwo * a.stride - a.pad;
+      const int ebase = ((pb * a.H + hb) * a.W + wb) * a.Cin;
       const uint32_t dst = a_raw(s) + soff;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int h = hb + kh[c], w = wb + kw[c];
         const bool ok = pok && kok[c] && h >= 0 && h < a.H && w >= 0 && w < a.W;
-        const float* src = ok ? a.x + (((long)b * a.H + h) * a.W + w) * a.Cin + cc[c] + j * 4 : a.x;
-        cp_async16(dst + c * BLK, src, ok ? 16u : 0u);
+        cp_async16(dst + c * BLK, a.x + (ok ? ebase + tapoff[c] : 0), ok ? 16u : 0u);
       }
+      pwo += BP;
+      while (pwo >= a.Wo) { pwo -= a.Wo; if (++pho == a.Ho) { pho = 0; ++pb; } }
       if (groups) cp_async_commit();
       else cp_async_arrive_noinc(landed_bar(s));
     }
@@ -396,17 +408,17 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
       if (lane == 0)
         for (int it = nst > 2 ? nst - 2 : 0; it < nst; ++it) mbar_arrive(landed_bar(it % C::STAGES));
     }
-  } else if (warp < NLOADW + 4) {
+  } else if (warp < WG_MMA_WARP) {
     // ======================= splitters, then epilogue =======================
     const int t = tid - NLOAD;
-    constexpr int NV = (C::A_BYTES + C::B_BYTES) / 16 / NSPLIT;     // float4 per thread per stage
+    constexpr int NV = (C::A_BYTES + C::B_BYTES) / 16 / WG_NSPLIT;  // float4 per thread per stage
     for (int it = 0; it < nst; ++it) {
       const int s = it % C::STAGES;
       mbar_wait(landed_bar(s), (it / C::STAGES) & 1);
       // (dY rows past `pend` meet all-zero A' rows, rows past M are zero-filled by the TMA unit)
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const uint32_t idx = (uint32_t)(t + NSPLIT * i);
+        const uint32_t idx = (uint32_t)(t + WG_NSPLIT * i);
         const bool isA = idx < C::A_BYTES / 16;
         const uint32_t so = (isA ? idx : idx - C::A_BYTES / 16) * 16u;
         const uint32_t src = (isA ? a_raw(s) : b_raw(s)) + so, dst = (isA ? a_lo(s) : b_lo(s)) + so;
@@ -430,24 +442,35 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
         mbar_arrive(full_bar(s));
       }
     }
-    const int ew = warp - NLOADW;
+    // epilogue: warp (q, half) owns k rows 32q..32q+31 and the 16-column chunks half, half+2, ...
+    const int ew = warp - NLOADW, q = ew & 3, half = ew >> 2;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const int k = k0 + ew * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16);
+    const int k = k0 + q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nmain = nst < C::NMAIN ? nst : C::NMAIN;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      float acc[16], tmp[16];
-      tmem_ld16(trow + (uint32_t)(BN + c), acc);
-      for (int q = 1; q < nmain; ++q) {
-        tmem_ld16(trow + (uint32_t)((1 + q) * BN + c), tmp);
+    for (int c = half * 16; c < BN; c += 32) {
+      // accumulators in summation order: main 0..nmain-1, then the correction terms
+      float acc[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] += tmp[e];
+      for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+      for (int g = 0; g <= nmain; g += 4) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = g + u;
+          if (i <= nmain) tmem_ld16_nowait(trow + (uint32_t)((i < nmain ? (1 + i) * BN : 0) + c), v[u]);
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (g + u <= nmain) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(v[u][e]);
+          }
+        }
       }
-      tmem_ld16(trow + (uint32_t)c, tmp);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) acc[e] += tmp[e];
       if (a.dbg == 1) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[e] = 1.0f;
@@ -457,6 +480,19 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
         for (int e = 0; e < 16; ++e)
           if (n0 + c + e < a.N) atomicAdd(a.dw + (long)(n0 + c + e) * a.K + k, acc[e]);
       }
+    }
+  } else if (warp == WG_TMA_WARP) {
+    // ======================= dY tiles by TMA =======================
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % C::STAGES;
+      if (it >= C::STAGES) mbar_wait(empty_bar(s), ((it / C::STAGES) - 1) & 1);
+      if (elect_one()) {
+        const int p0 = pbeg + it * BP;
+        mbar_expect_tx(landed_bar(s), C::B_BYTES);
+#pragma unroll
+        for (int nb = 0; nb < C::NB; ++nb) tma_load_2d(b_raw(s) + nb * BLK, &tm_dy, n0 + 32 * nb, p0, landed_bar(s));
+      }
+      __syncwarp();
     }
   } else {
     // ======================= MMA issuer =======================
@@ -488,7 +524,7 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == NLOADW + 4) {
+  if (warp == WG_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "n"(C::TMEM_COLS)
@@ -583,7 +619,7 @@ int launch_wgrad_tc(const WgTcArgs& a0, const float* dy, cudaStream_t st) {
   a.p_per_split = fd::cdiv(fd::cdiv(a.M, splits), BP) * BP;
   splits = fd::cdiv(a.M, a.p_per_split);
   dim3 grid(fd::cdiv(a.K, 128), a.N / BN, splits);
-  conv_wgrad_tc_kernel<BN><<<grid, NTHREADS, C::SMEM, st>>>(a, tdy);
+  conv_wgrad_tc_kernel<BN><<<grid, WG_NTHREADS, C::SMEM, st>>>(a, tdy);
   FD_CHECK_LAUNCH();
   return 0;
 }
@@ -676,6 +712,7 @@ int fd_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H,
   a.N = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
   long M = (long)B * a.Ho * a.Wo;
   FD_REQUIRE(M < (1L << 31), "fd_conv2d_wgrad_tc: too many pixels");
+  FD_REQUIRE((long)B * H * W * Cin < (1L << 31), "fd_conv2d_wgrad_tc: input has 2^31 or more elements");
   a.M = (int)M;
   a.K = KH * KW * Cin;
   a.p_per_split = 0;

@@ -24,8 +24,9 @@ namespace {
 
 constexpr int NLOADW2 = 4, NLOAD2 = NLOADW2 * 32;
 constexpr int NSPLITW2 = 8, NSPLIT2 = NSPLITW2 * 32;
-constexpr int NTHREADS2 = NLOAD2 + NSPLIT2 + 32;
+constexpr int NTHREADS2 = NLOAD2 + NSPLIT2 + 64;       // + the MMA warp + the weight-tile (TMA) warp
 constexpr int MMA_WARP2 = NLOADW2 + NSPLITW2;
+constexpr int TMA_WARP2 = MMA_WARP2 + 1;
 constexpr int LOOKAHEAD = 2;                     // cp.async groups a loader keeps in flight (< STAGES)
 
 // Timing experiment (FD_TC2_FLAGS bit 7): CTA (0,0) records clock64() at the hand-off points of one
@@ -46,7 +47,7 @@ struct Cfg2 {
   static constexpr int ACC0 = TST * 64;                                 // first accumulator column
   static constexpr int NACC = (512 - ACC0) / BN > 8 ? 8 : (512 - ACC0) / BN;
   static constexpr int NMAIN = NACC - 1;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/ + 1536 /*row table*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row table*/;
 };
 
 template <int BN, int MODE>
@@ -77,10 +78,10 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   // Row table: tile row r -> (pointer to the first gathered channel of its pixel, valid-tap mask).
   // One row per loader thread, published through shared memory by the prologue barrier -- not eight
   // rows of integer divisions per thread in front of the first load (measured: 6.7k cycles per CTA).
-  const uint32_t tab_ptr = bars + 512u, tab_mask = tab_ptr + 8u * BM;
+  const uint32_t tab_ptr = bars + 512u, tab_mask = tab_ptr + 4u * BM;
   if (tid < BM) {
     const long m = m0 + tid;
-    const float* ptr = a.x;
+    int eoff = 0;                      // element offset of the pixel's first gathered channel (may be < 0)
     uint32_t mask = 0;
     if (m < a.M) {
       const uint32_t HoWo = (uint32_t)(a.Ho * a.Wo);
@@ -111,9 +112,9 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           mask |= (uint32_t)(tw >= 0 && al && tq < a.Wg) << (8 + t);
         }
       }
-      ptr = a.x + (((long)b * a.Hg + hq) * a.Wg + wq) * a.Cg;
+      eoff = (int)((((long)b * a.Hg + hq) * a.Wg + wq) * a.Cg);      // |x| < 2^31 elements (host check)
     }
-    asm volatile("st.shared.u64 [%0], %1;" ::"r"(tab_ptr + 8u * tid), "l"(ptr) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_ptr + 4u * tid), "r"(eoff) : "memory");
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_mask + 4u * tid), "r"(mask) : "memory");
   }
 
@@ -152,49 +153,42 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     constexpr int RSTEP = NLOAD2 / 8;               // 16 rows per pass
     constexpr int ROWS = BM / RSTEP;                // 8 rows per thread
     const int j = tid & 7, rg = tid >> 3;
-    const float* rp[ROWS];
+    int ro[ROWS];                                   // 32-bit element offsets: one IMAD.WIDE per copy
     uint32_t vm[ROWS];
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
       const uint32_t row = (uint32_t)(rg + RSTEP * i);
-      unsigned long long pv;
-      asm volatile("ld.shared.u64 %0, [%1];" : "=l"(pv) : "r"(tab_ptr + 8u * row));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ro[i]) : "r"(tab_ptr + 4u * row));
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vm[i]) : "r"(tab_mask + 4u * row));
-      rp[i] = reinterpret_cast<const float*>(pv) + j * 4;
+      ro[i] += j * 4;
     }
     // rows rg + 16 i share (row & 7) == (rg & 7)
     const uint32_t soff = (uint32_t)rg * 128u + (uint32_t)((j ^ (rg & 7)) << 4);
     int kh = 0, kw = 0, c0 = 0;
     const bool groups = (a.flags & 1) != 0;
+    const int look = ((a.flags >> 8) & 3) ? ((a.flags >> 8) & 3) : LOOKAHEAD;   // experiment: flags bits 8-9
     const bool tracing = trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
     for (int it = 0; it < nk; ++it) {
       const int s = it % C::STAGES;
       FD_TRACE(0, it, 0);
-      if (groups && it >= LOOKAHEAD) {           // the group issued LOOKAHEAD k-blocks ago has landed
-        cp_async_wait<LOOKAHEAD - 1>();
+      if (groups && it >= look) {                // the group issued `look` k-blocks ago has landed
+        if (look == 1) cp_async_wait<0>();
+        else if (look == 2) cp_async_wait<1>();
+        else cp_async_wait<2>();
         __syncwarp();
-        if (elect_one()) mbar_arrive(landed_bar((it - LOOKAHEAD) % C::STAGES));
+        if (elect_one()) mbar_arrive(landed_bar((it - look) % C::STAGES));
       }
       FD_TRACE(0, it, 1);
       if (it >= C::STAGES) mbar_wait(sfree_bar(s), ((it / C::STAGES) - 1) & 1);
       FD_TRACE(0, it, 2);
-      if (warp == 0 && elect_one()) {
-        if (a.flags & 8) {                       // timing experiment: no loads at all
-          mbar_arrive(landed_bar(s));
-        } else {
-          mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
-          tma_load_2d(b_raw(s), &tm_w, it * BK, n0, landed_bar(s));
-          tma_load_2d(b_lo(s), &tm_wlo, it * BK, n0, landed_bar(s));
-        }
-      }
-      const long toff = MODE == 0 ? ((long)kh * a.Wg + kw) * a.Cg + c0
-                                  : -((long)(kh / a.stride) * a.Wg + kw / a.stride) * a.Cg + c0;
+      const int toff = MODE == 0 ? (kh * a.Wg + kw) * a.Cg + c0
+                                 : -((kh / a.stride) * a.Wg + kw / a.stride) * a.Cg + c0;
       const uint32_t dst = a_smem(s) + soff;
       if (!(a.flags & 8)) {
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
           const bool ok = ((vm[i] >> kh) & (vm[i] >> (8 + kw)) & 1u) != 0;
-          cp_async16(dst + (uint32_t)i * RSTEP * 128u, ok ? rp[i] + toff : a.x, ok ? 16u : 0u);
+          cp_async16(dst + (uint32_t)i * RSTEP * 128u, a.x + (ok ? ro[i] + toff : 0), ok ? 16u : 0u);
         }
       }
       if (groups) cp_async_commit();
@@ -207,7 +201,7 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       cp_async_wait<0>();
       __syncwarp();
       if (lane == 0)
-        for (int it = nk > LOOKAHEAD ? nk - LOOKAHEAD : 0; it < nk; ++it) mbar_arrive(landed_bar(it % C::STAGES));
+        for (int it = nk > look ? nk - look : 0; it < nk; ++it) mbar_arrive(landed_bar(it % C::STAGES));
     }
   } else if (warp < MMA_WARP2) {
     // ======================= splitters, then epilogue =======================
@@ -296,6 +290,22 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
       }
     }
+  } else if (warp == TMA_WARP2) {
+    // ======================= weight tiles: W and W_lo by TMA =======================
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % C::STAGES;
+      if (it >= C::STAGES) mbar_wait(sfree_bar(s), ((it / C::STAGES) - 1) & 1);
+      if (elect_one()) {
+        if (a.flags & 8) {                       // timing experiment: no loads at all
+          mbar_arrive(landed_bar(s));
+        } else {
+          mbar_expect_tx(landed_bar(s), 2 * C::B_TILE);
+          tma_load_2d(b_raw(s), &tm_w, it * BK, n0, landed_bar(s));
+          tma_load_2d(b_lo(s), &tm_wlo, it * BK, n0, landed_bar(s));
+        }
+      }
+      __syncwarp();
+    }
   } else {
     // ======================= MMA issuer =======================
     // The whole warp walks the loop and waits on the barriers (converged); one lane issues.  A lone
@@ -381,6 +391,7 @@ int dispatch_tc2(const TcArgs& a, cudaStream_t st) {
              "conv_tc2: operands must be 16-byte aligned");
   FD_REQUIRE(a.M < (1L << 31) && a.KH <= 8 && a.KW <= 8, "conv_tc2: problem too large (M=%ld, %dx%d)", a.M,
              a.KH, a.KW);
+  FD_REQUIRE((long)a.B * a.Hg * a.Wg * a.Cg < (1L << 31), "conv_tc2: gathered tensor has 2^31 or more elements");
   static int narrow_below = -1;        // FD_TC2_NARROW: CTA-count threshold below which N=128 layers use N=64 tiles
   if (narrow_below < 0) {
     const char* e = getenv("FD_TC2_NARROW");

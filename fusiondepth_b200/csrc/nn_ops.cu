@@ -35,24 +35,49 @@ __global__ void prep_input_kernel(const float* __restrict__ x, float* __restrict
 // ---- 7x7/2 stem as a GEMM: normalised im2col rows ------------------------------------------------
 // A[m][k], m = (b,ho,wo), k = (kh*KW + kw)*C + c for k < KH*KW*C, zero up to Kpad (a multiple of 32 so
 // the tensor-core 1x1 path takes it).  Values are (x - mean)/std inside the image, 0 in the padding.
-__global__ void stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ A, int C, int H, int W,
-                                   int Ho, int Wo, int KH, int KW, int stride, int pad, int Kpad,
-                                   float mean, float stdv, long total) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int k = (int)(i % Kpad);
-    long m = i / Kpad;
+// One block per (image, output row): the KH input rows it touches are normalised once into shared
+// memory (zero columns on both sides stand in for the padding), then thread (k quad, pixel lane)
+// streams float4 rows of A with four shared-memory loads each -- the index arithmetic is hoisted out
+// of the pixel loop and every input element is divided by std once instead of once per tap.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ A,
+                                                          int C, int H, int W, int Ho, int Wo, int KH, int KW,
+                                                          int stride, int pad, int Kpad, float mean, float stdv) {
+  extern __shared__ float sm[];                       // [C][KH][Wp]
+  const int b = blockIdx.y, ho = blockIdx.x, t = threadIdx.x;
+  const int Wp = W + 2 * pad, rowlen = KH * Wp;
+  for (int idx = t; idx < C * rowlen; idx += blockDim.x) {
+    const int c = idx / rowlen, r = idx - c * rowlen;
+    const int kh = r / Wp, w = r - kh * Wp - pad;
+    const int h = ho * stride - pad + kh;
     float v = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W)
+      v = __fdiv_rn(__fadd_rn(x[(((long)b * C + c) * H + h) * W + w], -mean), stdv);
+    sm[idx] = v;
+  }
+  __syncthreads();
+  const int Kq = Kpad >> 2, G = blockDim.x / Kq;
+  const int q = t % Kq, g = t / Kq;
+  if (g >= G) return;
+  int off[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = 4 * q + e;
+    off[e] = -1;
     if (k < KH * KW * C) {
-      int c = k % C, tap = k / C;
-      int kh = tap / KW, kw = tap - kh * KW;
-      int wo = (int)(m % Wo);
-      long t = m / Wo;
-      int ho = (int)(t % Ho), b = (int)(t / Ho);
-      int h = ho * stride - pad + kh, w = wo * stride - pad + kw;
-      if (h >= 0 && h < H && w >= 0 && w < W)
-        v = __fdiv_rn(__fadd_rn(x[(((long)b * C + c) * H + h) * W + w], -mean), stdv);
+      const int c = k % C, tap = k / C;
+      const int kh = tap / KW, kw = tap - kh * KW;
+      off[e] = (c * KH + kh) * Wp + kw;
     }
-    A[i] = v;
+  }
+  float* row = A + ((long)(b * Ho + ho) * Wo) * Kpad + 4 * q;
+  for (int wo = g; wo < Wo; wo += G) {
+    const int xo = wo * stride;
+    float4 v;
+    v.x = off[0] >= 0 ? sm[off[0] + xo] : 0.f;
+    v.y = off[1] >= 0 ? sm[off[1] + xo] : 0.f;
+    v.z = off[2] >= 0 ? sm[off[2] + xo] : 0.f;
+    v.w = off[3] >= 0 ? sm[off[3] + xo] : 0.f;
+    *reinterpret_cast<float4*>(row + (long)wo * Kpad) = v;
   }
 }
 
@@ -557,9 +582,17 @@ int fd_stem_im2col(const float* x_nchw, float* A, int B, int C, int H, int W, in
                    int pad, int Kpad, float mean, float stdv, void* stream) {
   FD_REQUIRE(Kpad >= KH * KW * C && Kpad % 4 == 0, "fd_stem_im2col: bad Kpad %d", Kpad);
   int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  long total = (long)B * Ho * Wo * Kpad;
-  stem_im2col_kernel<<<min(fd::cdiv(total, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-      x_nchw, A, C, H, W, Ho, Wo, KH, KW, stride, pad, Kpad, mean, stdv, total);
+  const size_t smem = (size_t)C * KH * (W + 2 * pad) * sizeof(float);
+  FD_REQUIRE(Kpad <= 1024 && smem <= 220 * 1024, "fd_stem_im2col: Kpad %d / %zu B of row staging not supported",
+             Kpad, smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    FD_REQUIRE(e == cudaSuccess, "fd_stem_im2col: cannot reserve shared memory: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  stem_im2col_kernel<<<dim3(Ho, B), 256, smem, (cudaStream_t)stream>>>(x_nchw, A, C, H, W, Ho, Wo, KH, KW, stride,
+                                                                     pad, Kpad, mean, stdv);
   FD_CHECK_LAUNCH();
   return 0;
 }

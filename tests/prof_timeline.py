@@ -25,15 +25,18 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", sys.argv[1] if len(sys.argv) > 1 else "timeline.csv")
 os.makedirs(os.path.dirname(out), exist_ok=True)
+import json, tempfile
+tmp = tempfile.mktemp(suffix=".json")
+prof.export_chrome_trace(tmp)
 n = 0
 with open(out, "w") as f:
-    f.write("name,stream,start_us,dur_us\n")
-    for ev in prof.events():
-        if ev.device_type == torch.autograd.DeviceType.CUDA:
-            name = ev.name.replace(",", ";")
-            stream = getattr(ev, "stream", None)
-            if stream is None:
-                stream = ev.device_resource_id if hasattr(ev, "device_resource_id") else -1
-            f.write("%s,%s,%.3f,%.3f\n" % (name[:100], stream, ev.time_range.start, ev.time_range.end - ev.time_range.start))
+    f.write("name,stream,start_us,dur_us,ctas,threads,smem,regs\n")
+    for ev in json.load(open(tmp))["traceEvents"]:
+        if ev.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy") and "dur" in ev:
+            a = ev.get("args", {})
+            g, b = a.get("grid", [0, 0, 0]), a.get("block", [0, 0, 0])
+            f.write("%s,%s,%.3f,%.3f,%d,%d,%d,%d\n" % (
+                ev["name"].replace(",", ";")[:100], a.get("stream", -1), ev["ts"], ev["dur"],
+                g[0] * g[1] * g[2], b[0] * b[1] * b[2], a.get("shared memory", 0), a.get("registers per thread", 0)))
             n += 1
 print("wrote", n, "device events to", out)
