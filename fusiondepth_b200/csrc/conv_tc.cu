@@ -331,7 +331,7 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
     for (int s = 0; s < C::STAGES; ++s) {
       // elected per-warp arrivals (flags bit 0): 32 lanes arriving on one mbarrier serialise
       mbar_init(landed_bar(s), ((a.flags & 1) ? NLOADW : NLOAD) + 1);
-      mbar_init(full_bar(s), (a.flags & 1) ? WG_NSPLITW : WG_NSPLIT);
+      mbar_init(full_bar(s), WG_NSPLITW);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
@@ -435,12 +435,8 @@ conv_wgrad_tc_kernel(WgTcArgs a, const __grid_constant__ CUtensorMap tm_dy) {
                      : "memory");
       }
       fence_async_proxy();
-      if (a.flags & 1) {
-        __syncwarp();
-        if (elect_one()) mbar_arrive(full_bar(s));
-      } else {
-        mbar_arrive(full_bar(s));
-      }
+      __syncwarp();
+      if (elect_one()) mbar_arrive(full_bar(s));
     }
     // epilogue: warp (q, half) owns k rows 32q..32q+31 and the 16-column chunks half, half+2, ...
     const int ew = warp - NLOADW, q = ew & 3, half = ew >> 2;
@@ -631,7 +627,7 @@ static int tc2_flags() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("FD_TC2_FLAGS");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }

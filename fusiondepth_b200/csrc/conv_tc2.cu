@@ -45,8 +45,13 @@ struct Cfg2 {
   static constexpr int STAGES = BN == 128 ? 4 : (BN == 64 ? 6 : 8);
   static constexpr int TST = BN == 128 ? 2 : (BN == 64 ? 3 : 4);      // TMEM A-ring slots
   static constexpr int ACC0 = TST * 64;                                 // first accumulator column
-  static constexpr int NACC = (512 - ACC0) / BN > 8 ? 8 : (512 - ACC0) / BN;
-  static constexpr int NMAIN = NACC - 1;
+  // PAIR (BN <= 64): W and W_lo sit back to back in the stage, so ONE N = 2*BN MMA computes A*W (main)
+  // and A*W_lo (correction) into a [main | corr2] accumulator pair: 8 MMAs per k-block instead of 12
+  // (the issuing thread, ~40 cycles per tcgen05.mma, paces the narrow tiles).  A_lo*W keeps its own
+  // accumulator.  BN = 128 has no TMEM for pairs and is MMA-execution bound anyway.
+  static constexpr bool PAIR = BN <= 64;
+  static constexpr int NMAIN_ = PAIR ? (512 - ACC0 - BN) / (2 * BN) : (512 - ACC0) / BN - 1;
+  static constexpr int NMAIN = NMAIN_ > 7 ? 7 : NMAIN_;
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row table*/;
 };
 
@@ -125,10 +130,10 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       // landed: 1 expect_tx arrive + either one arrival per loader warp (cp.async groups, flags bit 0)
       // or one asynchronous cp.async.mbarrier arrival per loader thread
       mbar_init(landed_bar(s), ((a.flags & 1) ? NLOADW2 : NLOAD2) + 1);
-      mbar_init(sfree_bar(s), NSPLITW2 + 1);   // every splitter warp has read A + the MMAs have read B
+      mbar_init(sfree_bar(s), NSPLITW2 / 2 + 1);   // the 4 splitter warps of this k-block + the MMAs' commit
     }
     for (int t = 0; t < C::TST; ++t) {
-      mbar_init(tfull_bar(t), NSPLITW2);
+      mbar_init(tfull_bar(t), NSPLITW2 / 2);
       mbar_init(tfree_bar(t), 1);
     }
     mbar_init(acc_bar, 1);
@@ -205,31 +210,33 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     }
   } else if (warp < MMA_WARP2) {
     // ======================= splitters, then epilogue =======================
+    // Two groups of four warps take alternate k-blocks (thread = one whole tile row of 32 channels):
+    // the barrier waits, fences and TMEM-store round trip of a k-block cost ~900 cycles of latency
+    // per warp whatever the payload, so each group gets two k-block periods to hide them.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int half = (warp - NLOADW2) >> 2;       // which 16 of the 32 channels of a k-block
+    const int half = (warp - NLOADW2) >> 2;       // splitter group (k-block parity); column half in the epilogue
     const int row = q * 32 + lane;
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool tracing = trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && tid == NLOAD2;
-    for (int kb = 0; kb < nk; ++kb) {
+    for (int kb = half; kb < nk; kb += 2) {
       const int s = kb % C::STAGES, t = kb % C::TST;
       FD_TRACE(1, kb, 0);
       mbar_wait(landed_bar(s), (kb / C::STAGES) & 1);
       FD_TRACE(1, kb, 1);
-      uint32_t hi[16], lo[16];
+      uint32_t hi[32], lo[32];
       const uint32_t ar = a_smem(s) + row_off;
       const bool skip_split = (a.flags & 4) != 0;      // timing experiment: hand-offs only
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
+      for (int jj = 0; jj < 8; ++jj) {
         if (skip_split) { hi[4 * jj] = hi[4 * jj + 1] = hi[4 * jj + 2] = hi[4 * jj + 3] = 0u; continue; }
-        const uint32_t chunk = (uint32_t)(half * 4 + jj);
         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(hi[4 * jj]), "=r"(hi[4 * jj + 1]), "=r"(hi[4 * jj + 2]), "=r"(hi[4 * jj + 3])
-                     : "r"(ar + ((chunk ^ sw) << 4)));
+                     : "r"(ar + (((uint32_t)jj ^ sw) << 4)));
       }
 #pragma unroll
-      for (int e = 0; e < 16; ++e) lo[e] = __float_as_uint(lo_part(__uint_as_float(hi[e])));
+      for (int e = 0; e < 32; ++e) lo[e] = __float_as_uint(lo_part(__uint_as_float(hi[e])));
       // the warp is converged: once the low parts are computed every lane's loads have returned
       __syncwarp();
       if (elect_one()) mbar_arrive(sfree_bar(s));
@@ -238,10 +245,12 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         tc_fence_after();
       }
       FD_TRACE(1, kb, 2);
-      const uint32_t tcol = tlane + (uint32_t)(t * 64 + half * 16);
+      const uint32_t tcol = tlane + (uint32_t)(t * 64);
       if (!skip_split) {
-        tmem_st16(tcol, hi);
-        tmem_st16(tcol + 32u, lo);
+        tmem_st16(tcol, *reinterpret_cast<const uint32_t(*)[16]>(&hi[0]));
+        tmem_st16(tcol + 16u, *reinterpret_cast<const uint32_t(*)[16]>(&hi[16]));
+        tmem_st16(tcol + 32u, *reinterpret_cast<const uint32_t(*)[16]>(&lo[0]));
+        tmem_st16(tcol + 48u, *reinterpret_cast<const uint32_t(*)[16]>(&lo[16]));
         tmem_wait_st();
       }
       tc_fence_before();
@@ -262,17 +271,22 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       float acc[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-      for (int g = 0; g <= nmain; g += 4) {
+      // list of accumulator column bases: PAIR: main_0, corr2_0, main_1, ... then corr1; else main_i, corr
+      const int nacc = C::PAIR ? 2 * nmain + 1 : nmain + 1;
+      for (int g = 0; g < nacc; g += 4) {
         uint32_t v[4][16];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = g + u;
-          if (i <= nmain) tmem_ld16_nowait(trow + (uint32_t)((i < nmain ? (1 + i) * BN : 0) + c), v[u]);
+          if (i < nacc) {
+            const int col = i == nacc - 1 ? 0 : (C::PAIR ? BN + i * BN : (1 + i) * BN);
+            tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);
+          }
         }
         tmem_wait_ld();
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (g + u <= nmain) {
+          if (g + u < nacc) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(v[u][e]);
           }
@@ -314,6 +328,8 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     const bool tracing = trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);                    // N = 2*BN: [W ; W_lo]
     const uint32_t d_corr = tmem_base + (uint32_t)C::ACC0;
     for (int kb = 0; kb < nk; ++kb) {
       const int s = kb % C::STAGES, t = kb % C::TST;
@@ -325,15 +341,25 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       if (elect_one()) {
         const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
         const uint32_t ta = tmem_base + (uint32_t)(t * 64), tal = ta + 32u;
-        const uint32_t d_main = d_corr + (uint32_t)((1 + kb % C::NMAIN) * BN);
+        if (C::PAIR) {
+          const uint32_t d_pair = d_corr + (uint32_t)(BN + (kb % C::NMAIN) * 2 * BN);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);
-          if (!(a.flags & (2 | 16))) {
-            umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
-            umma_tf32_ts(d_corr, ta + 8u * k, dbl + adv, idesc, 1);
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            if (!(a.flags & (2 | 16))) umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+            if (!(a.flags & 16)) umma_tf32_ts(d_pair, ta + 8u * k, db + adv, idesc2, (kb >= C::NMAIN) || (k != 0));
           }
-          if (!(a.flags & 16)) umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
+        } else {
+          const uint32_t d_main = d_corr + (uint32_t)((1 + kb % C::NMAIN) * BN);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            if (!(a.flags & (2 | 16))) {
+              umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+              umma_tf32_ts(d_corr, ta + 8u * k, dbl + adv, idesc, 1);
+            }
+            if (!(a.flags & 16)) umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
+          }
         }
         if (plain) {
           mbar_arrive(sfree_bar(s));
