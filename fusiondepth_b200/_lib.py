@@ -66,6 +66,7 @@ _SIGNATURES = {
     "fd_conv2d_tc_supported": (c_int, [_I, _I]),
     "fd_tf32_split": (c_int, [_P, _P, _L, _P]),
     "fd_weight_transpose_split": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "fd_weight_transpose_split_batched": (c_int, [_P, _P, _P, _P, _I, _L, _P]),
     "fd_conv2d_fwd_tc": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_dgrad_tc": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_wgrad_tc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

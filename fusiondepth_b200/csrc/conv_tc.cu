@@ -549,6 +549,33 @@ __global__ void transpose_split_kernel(const float* __restrict__ w, float* __res
   }
 }
 
+// The same for every conv weight of a flat parameter buffer in one launch.  desc[j] = {first output
+// element of tensor j in the concatenated index space, offset of the tensor in the flat buffers,
+// Cout, taps, Cin}; outputs keep the tensor's offset.
+__global__ void transpose_split_batched_kernel(const float* __restrict__ flat, float* __restrict__ flat_t,
+                                               float* __restrict__ flat_tlo, const long* __restrict__ desc,
+                                               int n, long total) {
+  extern __shared__ long starts[];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) starts[j] = desc[5 * j];
+  __syncthreads();
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {                       // last j with starts[j] <= i
+      const int mid = (lo + hi + 1) >> 1;
+      if (starts[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const long* d = desc + 5 * lo;
+    const long off = d[1];
+    const int Cout = (int)d[2], taps = (int)d[3], Cin = (int)d[4];
+    const int li = (int)(i - d[0]);
+    const int co = li % Cout;
+    const int tp = (li / Cout) % taps;
+    const int ci = li / (Cout * taps);
+    const float v = flat[off + ((long)co * taps + tp) * Cin + ci];
+    flat_t[off + li] = v;
+    flat_tlo[off + li] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+}
 
 template <int BN, int MODE>
 int launch_tc(const TcArgs& a, cudaStream_t st) {
@@ -655,6 +682,15 @@ int fd_weight_transpose_split(const float* w, float* wt, float* wt_lo, int Cout,
   long n = (long)Cout * taps * Cin;
   transpose_split_kernel<<<min(fd::cdiv(n, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(
       w, wt, wt_lo, Cout, taps, Cin);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_weight_transpose_split_batched(const float* flat, float* flat_t, float* flat_tlo, const long* desc,
+                                      int n, long total, void* stream) {
+  FD_REQUIRE(n > 0 && n <= 4096, "fd_weight_transpose_split_batched: %d tensors", n);
+  transpose_split_batched_kernel<<<min(fd::cdiv(total, 256), 148 * 16), 256, n * sizeof(long),
+                                   (cudaStream_t)stream>>>(flat, flat_t, flat_tlo, desc, n, total);
   FD_CHECK_LAUNCH();
   return 0;
 }

@@ -6,6 +6,8 @@
 // All kernels map threadIdx.x to the channel (fastest) dimension so every warp access is a
 // contiguous 128 B line; reductions over pixels accumulate in fp64 so the batch statistics match
 // the reference's two-pass CPU result to fp32 rounding.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/fusiondepth_b200.h"
 
@@ -380,6 +382,188 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// ---- small-M BatchNorm: one kernel per direction ----------------------------------------------
+// layer4 tensors (M = B*H*W <= 1024 rows) are a few hundred KB: two or three dependent
+// launches with fp64 atomics in between cost ~12 us each in launch + DRAM latency.  Here a CTA owns 8
+// channels for ALL rows, so the batch statistics never leave the block: pass 1 reduces, pass 2
+// re-reads the (L1/L2-resident) columns and writes.  Thread = (channel quad, row lane).
+constexpr int BNF_CG = 8;                 // channels per CTA
+constexpr int BNF_LANES = 256 / (BNF_CG / 4);
+
+__device__ __forceinline__ void bnf_block_reduce(double (&s)[4], double (&ss)[4], double* red, int cq, int rl) {
+  // red: [BNF_LANES][BNF_CG/4][8] doubles; result (all row lanes summed) returned to every thread
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[(rl * (BNF_CG / 4) + cq) * 8 + i] = s[i];
+    red[(rl * (BNF_CG / 4) + cq) * 8 + 4 + i] = ss[i];
+  }
+  __syncthreads();
+  for (int stride = BNF_LANES / 2; stride > 0; stride >>= 1) {
+    if (rl < stride) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        red[(rl * (BNF_CG / 4) + cq) * 8 + i] += red[((rl + stride) * (BNF_CG / 4) + cq) * 8 + i];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s[i] = red[cq * 8 + i]; ss[i] = red[cq * 8 + 4 + i]; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) bn_fwd_fused_kernel(
+    const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* running_mean, float* running_var, int training, float momentum,
+    float eps, float stat_weight, float* save_mean, float* save_rstd, int relu, float* __restrict__ y, int M,
+    int C) {
+  extern __shared__ double red[];
+  const int cq = threadIdx.x % (BNF_CG / 4), rl = threadIdx.x / (BNF_CG / 4);
+  const int c = blockIdx.x * BNF_CG + cq * 4;
+  float mu[4], rs[4];
+  if (training) {
+    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    for (int m0 = rl; m0 < M; m0 += BNF_LANES * 8) {
+      float ps[4] = {0.f, 0.f, 0.f, 0.f}, pss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int m = m0 + j * BNF_LANES;
+        if (m < M) {
+          float v[4];
+          ldv<4>(x + (long)m * C + c, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { ps[i] += v[i]; pss[i] = fmaf(v[i], v[i], pss[i]); }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s[i] += (double)ps[i]; ss[i] += (double)pss[i]; }
+    }
+    bnf_block_reduce(s, ss, red, cq, rl);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double mean = s[i] / (double)M;
+      double var = ss[i] / (double)M - mean * mean;
+      if (var < 0) var = 0;
+      mu[i] = (float)mean;
+      rs[i] = (float)(1.0 / sqrt(var + (double)eps));
+      if (rl == 0) {
+        const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        if (stat_weight >= 0.f) {
+          atomicAdd(&running_mean[c + i], (float)((double)stat_weight * mean));
+          atomicAdd(&running_var[c + i], (float)((double)stat_weight * unb));
+        } else {
+          running_mean[c + i] = (float)((1.0 - momentum) * (double)running_mean[c + i] + (double)momentum * mean);
+          running_var[c + i] = (float)((1.0 - momentum) * (double)running_var[c + i] + (double)momentum * unb);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mu[i] = running_mean[c + i];
+      rs[i] = (float)(1.0 / sqrt((double)running_var[c + i] + (double)eps));
+    }
+  }
+  float g[4], bt[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    g[i] = gamma[c + i]; bt[i] = beta[c + i];
+    if (rl == 0) { save_mean[c + i] = mu[i]; save_rstd[c + i] = rs[i]; }
+  }
+  for (int m = rl; m < M; m += BNF_LANES) {
+    float v[4], r[4];
+    ldv<4>(x + (long)m * C + c, v);
+    if (res) ldv<4>(res + (long)m * C + c, r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float o = (v[i] - mu[i]) * rs[i] * g[i] + bt[i];
+      if (res) o += r[i];
+      if (relu) o = fmaxf(o, 0.f);
+      v[i] = o;
+    }
+    stv<4>(y + (long)m * C + c, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(
+    const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int relu,
+    int training, float* __restrict__ dx, float* __restrict__ dres, float* dgamma, float* dbeta, int M, int C,
+    int accumulate) {
+  extern __shared__ double red[];
+  const int cq = threadIdx.x % (BNF_CG / 4), rl = threadIdx.x / (BNF_CG / 4);
+  const int c = blockIdx.x * BNF_CG + cq * 4;
+  float mu[4], rs[4], gm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { mu[i] = mean[c + i]; rs[i] = rstd[c + i]; gm[i] = gamma[c + i]; }
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (int m0 = rl; m0 < M; m0 += BNF_LANES * 4) {
+    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + j * BNF_LANES;
+      if (m < M) {
+        float xv[4], yv[4], gv[4];
+        ldv<4>(x + (long)m * C + c, xv);
+        ldv<4>(dy + (long)m * C + c, gv);
+        if (relu) ldv<4>(y + (long)m * C + c, yv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float g = gv[i];
+          if (relu && !(yv[i] > 0.f)) g = 0.f;
+          ps[i] += g;
+          pss[i] = fmaf(g, (xv[i] - mu[i]) * rs[i], pss[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i] += (double)ps[i]; ss[i] += (double)pss[i]; }
+  }
+  bnf_block_reduce(s, ss, red, cq, rl);
+  float k1[4], k2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float sg = (float)s[i], sgx = (float)ss[i];
+    k1[i] = training ? sg / (float)M : 0.f;
+    k2[i] = training ? sgx / (float)M : 0.f;
+    if (rl == 0) {
+      if (accumulate) {
+        if (dgamma) atomicAdd(&dgamma[c + i], sgx);
+        if (dbeta) atomicAdd(&dbeta[c + i], sg);
+      } else {
+        if (dgamma) dgamma[c + i] = sgx;
+        if (dbeta) dbeta[c + i] = sg;
+      }
+    }
+  }
+  for (int m = rl; m < M; m += BNF_LANES) {
+    float xv[4], yv[4], gv[4];
+    ldv<4>(x + (long)m * C + c, xv);
+    ldv<4>(dy + (long)m * C + c, gv);
+    if (relu) ldv<4>(y + (long)m * C + c, yv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (relu && !(yv[i] > 0.f)) gv[i] = 0.f;
+    }
+    if (dres) stv<4>(dres + (long)m * C + c, gv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float xh = (xv[i] - mu[i]) * rs[i];
+      xv[i] = gm[i] * rs[i] * (gv[i] - k1[i] - xh * k2[i]);
+    }
+    stv<4>(dx + (long)m * C + c, xv);
+  }
+}
+
+static bool bn_fused_ok(long M, int C) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FD_BN_FUSED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && M <= 1024 && C % BNF_CG == 0;       // measured: no gain over the two-kernel form above ~1k rows
+}
+constexpr size_t BNF_SMEM = sizeof(double) * BNF_LANES * (BNF_CG / 4) * 8;
+
 // ---- max-pool 3x3 stride 2 pad 1 -------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                    unsigned char* __restrict__ idx, int H, int W, int C, int Ho,
@@ -619,6 +803,13 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
               float stat_weight, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn_fused_ok(M, C)) {
+    bn_fwd_fused_kernel<<<C / BNF_CG, 256, BNF_SMEM, st>>>(x, residual, gamma, beta, running_mean, running_var,
+                                                          training, momentum, eps, stat_weight, save_mean,
+                                                          save_rstd, relu, y, (int)M, C);
+    FD_CHECK_LAUNCH();
+    return 0;
+  }
   const int vec = (C % 4 == 0) ? 4 : 1;
   BnGeom g = bn_geom(M, C, vec);
   const size_t sm = sizeof(double) * 2 * vec * 256;
@@ -645,6 +836,12 @@ int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
               float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
               int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (bn_fused_ok(M, C)) {
+    bn_bwd_fused_kernel<<<C / BNF_CG, 256, BNF_SMEM, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
+                                                          dx, dresidual, dgamma, dbeta, (int)M, C, accumulate);
+    FD_CHECK_LAUNCH();
+    return 0;
+  }
   const int vec = (C % 4 == 0) ? 4 : 1;
   BnGeom g = bn_geom(M, C, vec);
   const size_t sm = sizeof(double) * 2 * vec * 256;

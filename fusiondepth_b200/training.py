@@ -14,6 +14,7 @@ Two ways in:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -215,6 +216,59 @@ class FlatParams:
             p._fd_grad = gv          # ops.DIRECT_GRAD: backward kernels add into this view
             off += (k + A - 1) // A * A
         self.numel = n
+        self.offsets = {}
+        off = 0
+        for p in params:
+            self.offsets[p] = off
+            off += (p.numel() + A - 1) // A * A
+        # derived conv-weight tensors (W_lo, W^T, W^T_lo) live in flat buffers with the same layout and
+        # are refreshed by two launches per optimiser step (prepare_weights)
+        self.lo = None
+        self.t = None
+        self.t_lo = None
+        self.t_desc = None
+        self.t_total = 0
+
+    def prepare_weights(self, cache: Dict):
+        """W_lo = W - tf32(W) for the whole buffer and the transposed copies (data-gradient operand) of
+        every tensor-core-eligible conv weight: two launches, then `cache` (ops.WEIGHT_CACHE) entries
+        keyed like ops.Conv2dFn's per-tensor path."""
+        from . import _lib
+        from ctypes import c_void_p
+        lib = _lib.load()
+        st = c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.lo is None:
+            self.lo = torch.empty_like(self.data)
+            rows, start = [], 0
+            self.t_params = []
+            for p in self.params:
+                if p.dim() == 4 and p.shape[0] % 32 == 0 and p.shape[1] % 16 == 0:
+                    o, i, kh, kw = p.shape
+                    rows.append([start, self.offsets[p], o, kh * kw, i])
+                    start += p.numel()
+                    self.t_params.append(p)
+            self.t_total = start
+            if rows:
+                self.t = torch.empty_like(self.data)
+                self.t_lo = torch.empty_like(self.data)
+                self.t_desc = torch.tensor(rows, dtype=torch.int64, device=self.data.device)
+        _lib.check(lib.fd_tf32_split(c_void_p(self.data.data_ptr()), c_void_p(self.lo.data_ptr()), self.numel, st),
+                   "fd_tf32_split")
+        if self.t_desc is not None:
+            _lib.check(lib.fd_weight_transpose_split_batched(
+                c_void_p(self.data.data_ptr()), c_void_p(self.t.data_ptr()), c_void_p(self.t_lo.data_ptr()),
+                c_void_p(self.t_desc.data_ptr()), self.t_desc.shape[0], self.t_total, st),
+                "fd_weight_transpose_split_batched")
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for p in self.params:
+            if p.dim() == 4:
+                off, k = self.offsets[p], p.numel()
+                cache[(p.data_ptr(), "lo")] = ((self.lo[off:off + k],), ev, cur)
+        for p in getattr(self, "t_params", []):
+            off, k = self.offsets[p], p.numel()
+            cache[(p.data_ptr(), "t")] = ((self.t[off:off + k], self.t_lo[off:off + k]), ev, cur)
 
     @staticmethod
     def _view(flat, p):
@@ -263,7 +317,8 @@ class TrainStep:
         # atomics, BatchNorm running statistics through ops.BNSchedule), so each gets its own stream
         # and trunk streams: while one micro-batch walks its serial decoder -> loss -> decoder
         # backward chain, the other one's trunks keep the SMs busy.
-        self.concurrent = bool(concurrent_microbatches) and accumulate > 1
+        self.concurrent = (bool(concurrent_microbatches) and accumulate > 1
+                           and os.environ.get("FD_CONCURRENT_MB", "1") != "0")
         nsets = accumulate if self.concurrent else 1
         self.trunks = [TrunkStreams(dev) if parallel_trunks else None for _ in range(nsets)]
         self.mb_streams = [torch.cuda.Stream(device=dev) for _ in range(nsets)] if self.concurrent else []
@@ -298,6 +353,8 @@ class TrainStep:
         try:
             if self.bn_schedule is not None:
                 self.bn_schedule.begin_step()
+            if self.cache_weight_prep and ops.CONV_BACKEND == "tc":
+                self.flat.prepare_weights(ops.WEIGHT_CACHE)
             out = self._run_inner(batches, noises)
             if self.bn_schedule is not None:
                 self.bn_schedule.end_step()

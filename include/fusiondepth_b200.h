@@ -130,6 +130,11 @@ int fd_weight_transpose(const float* w, float* wt, int Cout, int taps, int Cin, 
  * (fd_tf32_split); for the data gradient wt / wt_lo come from fd_weight_transpose_split. */
 int fd_conv2d_tc_supported(int gathered_channels, int produced_channels);
 int fd_tf32_split(const float* w, float* w_lo, long n, void* stream);
+/* ... for every conv weight of a flat parameter buffer in ONE launch: desc (device, int64 [n][5]) rows are
+ * {first element of tensor j in the concatenated index space, offset of tensor j in the flat buffers,
+ *  Cout, taps, Cin}; the transposed tensors land at the same offsets of flat_t / flat_tlo. */
+int fd_weight_transpose_split_batched(const float* flat, float* flat_t, float* flat_tlo, const long* desc,
+                                      int n, long total, void* stream);
 int fd_weight_transpose_split(const float* w, float* wt, float* wt_lo, int Cout, int taps, int Cin,
                               void* stream);
 int fd_conv2d_fwd_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,

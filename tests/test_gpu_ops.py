@@ -56,11 +56,14 @@ def test_conv2d_fwd_bwd(cuda, case):
         assert rel_err(bc.grad.cpu(), br.grad) < 5e-5
 
 
-@pytest.mark.parametrize("C,relu,res,training", [(64, True, False, True), (128, True, True, True),
-                                                 (20, False, False, True), (64, True, True, False)])
-def test_batch_norm(cuda, C, relu, res, training):
+@pytest.mark.parametrize("C,relu,res,training,hw", [
+    (64, True, False, True, (10, 14)), (128, True, True, True, (10, 14)), (20, False, False, True, (10, 14)),
+    (64, True, True, False, (10, 14)),
+    # M = 3*40*48 = 5760 > 1024 rows: the multi-kernel path (fp64 atomics); M = 420: one fused kernel
+    (64, True, True, True, (40, 48)), (32, False, False, True, (40, 48))])
+def test_batch_norm(cuda, C, relu, res, training, hw):
     from fusiondepth_b200 import ops
-    B, H, W = 3, 10, 14
+    B, (H, W) = 3, hw
     x = _rand((B, C, H, W), 1) * 2 + 0.5
     r = _rand((B, C, H, W), 2) if res else None
     gamma, beta = 0.5 + torch.rand(C, generator=torch.Generator().manual_seed(3)), _rand((C,), 4, 0.1)
