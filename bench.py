@@ -157,6 +157,50 @@ def run_reference(args):
     }))
 
 
+def ncu_traffic(which="conv"):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_traffic.json, written by profiles/ncu_table.py --traffic); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(which)
+    except Exception:
+        return None
+
+
+def dominant_kernel_leg(dev):
+    """The most frequent tensor-core conv of the step (ResNet layer1 3x3 64->64 on 6x48x160, 112 of
+    the ~390 conv_tc2 launches per step are this shape or its data gradient): average launch duration
+    over 3 x 20 back-to-back launches captured in a CUDA graph, CUDA events, inputs L2-warm."""
+    from fusiondepth_b200 import ops
+    CL = torch.channels_last
+    B, C, H, W = MICRO_B, 64, 48, 160
+    x = torch.randn(B, C, H, W, device=dev).contiguous(memory_format=CL)
+    w = torch.randn(C, C, 3, 3, device=dev).contiguous(memory_format=CL)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.no_grad():
+        with torch.cuda.stream(s):
+            ops.conv2d(x, w, None, 1, 1, "none")
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                ops.conv2d(x, w, None, 1, 1, "none")
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / 60
+    flop = 2.0 * B * H * W * C * C * 9
+    return {"kernel": "conv_tc2_kernel<64,0> (layer1 3x3 64->64, M=46080, K=576)", "avg_us": us,
+            "achieved_tflops": flop / (us * 1e-6) / 1e12, "mma_tflops_issued": 3 * flop / (us * 1e-6) / 1e12}
+
+
 def cpu_baseline_leg():
     """Bounded CPU sample on rank 0: one optimiser step (2 micro-batches of 6) after one warm-up
     micro-batch, through the oracle port."""
@@ -281,17 +325,29 @@ def run_ours(args):
     ms_e2e, _ = timed(e2e_step, args.steps)
     _phase("e2e done")
 
-    # per-kernel-family device times from one instrumented eager step on rank 0 alone, with the
-    # gradient all-reduce switched off (no collective may run on a single rank)
-    fam = {}
+    # Per-kernel-family device times: ONE instrumented eager step on rank 0, on a single stream (no
+    # trunk / micro-batch concurrency, no collective) with CUDA events around every conv and loss
+    # launch, so each event pair brackets one kernel running alone; the whole serial step is timed too.
+    fam, serial_ms, dom = {}, None, None
     if rank == 0:
         ops.PROFILE = {}
         step.world = 1
-        step.step(batches, noises)
+        keep = (step.trunks, step.concurrent)
+        step.trunks, step.concurrent = [None], False
+        step.step(batches, noises)                        # warm (allocator) on this code path
         torch.cuda.synchronize()
+        ops.PROFILE = {}
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step.step(batches, noises)
+        s1.record()
+        torch.cuda.synchronize()
+        serial_ms = s0.elapsed_time(s1)
         for name, evs in ops.PROFILE.items():
             fam[name] = (sum(s.elapsed_time(e) for s, e, _ in evs), sum(w for _, _, w in evs), len(evs))
         ops.PROFILE = None
+        step.trunks, step.concurrent = keep
+        dom = dominant_kernel_leg(dev)
     _phase("instrumented step done")
 
     result = None
@@ -303,14 +359,23 @@ def run_ours(args):
         pl_bytes = fam["photoloss_fwd"][1] + fam["photoloss_bwd"][1]
         conv_tf = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
         pl_gbs = pl_bytes / (pl_ms * 1e-3) / 1e9
-        roofline = {"kernel": "conv implicit-GEMM family (fwd+dgrad+wgrad), %d launches/step" % conv_n,
+        traffic = ncu_traffic()
+        roofline = {"kernel": "conv implicit-GEMM family (conv_tc2 fwd/dgrad + conv_wgrad_tc on tcgen05, "
+                              "small-channel CUDA-core kernels), %d launches/step" % conv_n,
                     "bound": "tensor", "achieved": conv_tf, "peak": pk["tf"], "unit": "TFLOP/s",
-                    "frac": conv_tf / pk["tf"], "traffic": None, "peak_source": pk["src"],
-                    "ms_per_step": conv_ms, "share_of_step": conv_ms / ms}
+                    "frac": conv_tf / pk["tf"], "traffic": traffic, "peak_source": pk["src"],
+                    "peak_note": "peak = measured dense bf16 cuBLAS; this path issues kind::tf32 MMAs (half the "
+                                 "bf16 rate) three times per product (3xTF32 for fp32 parity), so its ceiling "
+                                 "is peak/6",
+                    "frac_of_3xtf32_ceiling": conv_tf / (pk["tf"] / 6.0),
+                    "ms_per_step": conv_ms, "serial_step_ms": serial_ms,
+                    "share_of_serial_step": conv_ms / serial_ms if serial_ms else None,
+                    "dominant_kernel": dom}
         roofline_loss = {"kernel": "fd_photoloss_fwd+bwd (4 launches/step)", "bound": "hbm",
                          "achieved": pl_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": pl_gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"],
-                         "ms_per_step": pl_ms, "share_of_step": pl_ms / ms}
+                         "frac": pl_gbs / pk["hbm"], "traffic": ncu_traffic("photoloss"),
+                         "peak_source": pk["src"], "ms_per_step": pl_ms,
+                         "share_of_serial_step": pl_ms / serial_ms if serial_ms else None}
         result = {
             "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,

@@ -635,7 +635,16 @@ int launch_wgrad_tc(const WgTcArgs& a0, const float* dy, cudaStream_t st) {
   int rc = make_map_2d(&tdy, dy, a.M, a.N, BP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
   const int tiles = fd::cdiv(a.K, 128) * (a.N / BN);
-  int splits = (2 * 148 + tiles - 1) / tiles;
+  // pixel-range splits: enough CTAs for `waves` waves of 148 SMs.  A CTA pays ~8k cycles of prologue,
+  // pipeline fill and atomic epilogue whatever its share, so half a wave of longer CTAs beats two (measured 328 vs 310 img/s):
+  // the other streams of the step fill the remaining SMs.
+  static int waves_x2 = -1;                 // FD_WGRAD_WAVES (multiples of 0.5, default 0.5), kept as 2x integer
+  if (waves_x2 < 0) {
+    const char* e = getenv("FD_WGRAD_WAVES");
+    waves_x2 = e ? (int)(2.0 * atof(e) + 0.5) : 1;
+    if (waves_x2 < 1) waves_x2 = 1;
+  }
+  int splits = (waves_x2 * 74 + tiles - 1) / tiles;
   const int max_splits = fd::cdiv(a.M, 4 * BP);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -141,14 +141,18 @@ __device__ __forceinline__ void stv(float* p, const float (&v)[VEC]) {
 }
 
 struct BnGeom { int groups, gx, gy; dim3 grid, block; };
-inline BnGeom bn_geom(long M, int C, int vec) {
+// reduce = true: geometry of the two statistic kernels.  Their blocks end with 2*C fp64 atomics on the
+// same C addresses, which serialise in L2: a few dozen blocks stream the (L2-sized) tensor just as
+// fast and keep the contention per address small.
+inline BnGeom bn_geom(long M, int C, int vec, bool reduce = false) {
   BnGeom g;
   g.groups = C / vec;
   g.gx = g.groups < 32 ? g.groups : 32;          // channel groups per block row
   g.gy = 256 / g.gx;                              // pixel lanes per block
   int bx = (g.groups + g.gx - 1) / g.gx;
   long by = (M + (long)g.gy * 8 - 1) / ((long)g.gy * 8);
-  long cap = (148L * 8 + bx - 1) / bx;
+  long cap = reduce ? (48 + bx - 1) / bx : (148L * 8 + bx - 1) / bx;
+  if (reduce && cap < 8) cap = 8;
   if (by > cap) by = cap;
   if (by < 1) by = 1;
   g.grid = dim3(bx, (unsigned)by);
@@ -558,9 +562,9 @@ static bool bn_fused_ok(long M, int C) {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("FD_BN_FUSED");
-    on = (e && e[0] == '0') ? 0 : 1;
+    on = (e && e[0] == '1') ? 1 : 0;     // opt-in (FD_BN_FUSED=1): measured no faster than the two-kernel form
   }
-  return on && M <= 1024 && C % BNF_CG == 0;       // measured: no gain over the two-kernel form above ~1k rows
+  return on && M <= 1024 && C % BNF_CG == 0;
 }
 constexpr size_t BNF_SMEM = sizeof(double) * BNF_LANES * (BNF_CG / 4) * 8;
 
@@ -814,9 +818,10 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
   BnGeom g = bn_geom(M, C, vec);
   const size_t sm = sizeof(double) * 2 * vec * 256;
   if (training) {
+    BnGeom gr = bn_geom(M, C, vec, true);
     cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
-    if (vec == 4) bn_stats_kernel<4><<<g.grid, g.block, sm, st>>>(x, ws, M, C);
-    else bn_stats_kernel<1><<<g.grid, g.block, sm, st>>>(x, ws, M, C);
+    if (vec == 4) bn_stats_kernel<4><<<gr.grid, gr.block, sm, st>>>(x, ws, M, C);
+    else bn_stats_kernel<1><<<gr.grid, gr.block, sm, st>>>(x, ws, M, C);
     FD_CHECK_LAUNCH();
   }
   if (vec == 4)
@@ -846,13 +851,14 @@ int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
   BnGeom g = bn_geom(M, C, vec);
   const size_t sm = sizeof(double) * 2 * vec * 256;
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
+  BnGeom gr = bn_geom(M, C, vec, true);
   if (vec == 4) {
-    bn_bwd_reduce_kernel<4><<<g.grid, g.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
+    bn_bwd_reduce_kernel<4><<<gr.grid, gr.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
     FD_CHECK_LAUNCH();
     bn_bwd_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
                                                        ws, dx, dresidual, dgamma, dbeta, M, C, accumulate);
   } else {
-    bn_bwd_reduce_kernel<1><<<g.grid, g.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
+    bn_bwd_reduce_kernel<1><<<gr.grid, gr.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
     FD_CHECK_LAUNCH();
     bn_bwd_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
                                                        ws, dx, dresidual, dgamma, dbeta, M, C, accumulate);
