@@ -76,6 +76,10 @@ _SIGNATURES = {
     "fd_conv2d_cout1_dgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_cout1_wgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fd_debug_set_conv_trace": (c_int, [_P]),
+    "fd_conv2d_c16_supported": (c_int, [_I, _I, _I, _I, _I]),
+    "fd_conv2d_c16_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_conv2d_c16_dgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "fd_conv2d_c16_wgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fd_bn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P, _L, _I, _F, _P]),
     "fd_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "fd_maxpool3x3s2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -194,3 +194,198 @@ int fd_conv2d_cout1_wgrad(const float* x, const float* dy, float* dw, int B, int
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// 16-channel 3x3 layers at full / half resolution (DepthDecoder upconv(0,0) 32->16 and upconv(0,1)
+// 16->16, reference networks/depth_decoder.py:20-50 with num_ch_dec[0] = 16): direct convolutions on
+// the CUDA cores.  N = 16 output channels is one eighth of a tensor-core tile row and the generic
+// 128 x 64 implicit-GEMM tile wastes three quarters of its FMAs, while these layers hold the largest
+// pixel counts of the network (737k rows).
+//
+// direct3x3: out[b,h,w,:] = act(bias + sum_{kh,kw,ci} in[b, h+kh-off, w+kw-off, ci] * wk[kh][kw][ci][:])
+//   with zeros outside the input.  Forward: wk = W^T, off = pad.  Data gradient: in = dY, out = dX,
+//   wk[kh][kw][n][c] = W[n][2-kh][2-kw][c], off = 2 - pad.  Thread = PX consecutive pixels x all CO
+//   outputs; the weights sit in shared memory as [tap][ci][co] and every float4 of them (a warp-wide
+//   broadcast load) feeds 4*PX FMAs.
+// wgrad16: dW[n][kh][kw][c] += sum_p dY[p][n] * X[p + (kh,kw) - pad][c]; thread = (n, channel quad, kh)
+//   with a sliding 3-wide register window along the row; one block per slab of rows, atomics out.
+// ================================================================================================
+namespace {
+
+template <int CI, int CO, int PX, bool DGRAD>
+__global__ void __launch_bounds__(128) direct3x3_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        int B, int Hi, int Wi, int Ho, int Wo, int off, int act) {
+  __shared__ __align__(16) float wk[9 * CI * CO];
+  for (int i = threadIdx.x; i < 9 * CI * CO; i += blockDim.x) {
+    const int co = i % CO, ci = (i / CO) % CI, tap = i / (CO * CI);
+    // forward: W is [CO][9][CI];  data gradient: W is [n = CI][9][c = CO], taps flipped
+    wk[i] = DGRAD ? w[((long)ci * 9 + (8 - tap)) * CO + co] : w[((long)co * 9 + tap) * CI + ci];
+  }
+  __syncthreads();
+  const int wt_per_row = (Wo + PX - 1) / PX;
+  const long tiles = (long)B * Ho * wt_per_row;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < tiles; t += (long)gridDim.x * blockDim.x) {
+    const int wt = (int)(t % wt_per_row);
+    const long r = t / wt_per_row;
+    const int h = (int)(r % Ho), b = (int)(r / Ho);
+    const int w0 = wt * PX;
+    float acc[PX][CO];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+      for (int n = 0; n < CO; ++n) acc[p][n] = 0.f;
+#pragma unroll 1
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = h + kh - off;
+      if (hi < 0 || hi >= Hi) continue;
+      const float* rowp = in + ((long)b * Hi + hi) * Wi * CI;
+#pragma unroll 1
+      for (int cq = 0; cq < CI / 4; ++cq) {
+        float4 xin[PX + 2];
+#pragma unroll
+        for (int j = 0; j < PX + 2; ++j) {
+          const int wi = w0 + j - off;
+          xin[j] = (wi >= 0 && wi < Wi) ? *reinterpret_cast<const float4*>(rowp + (long)wi * CI + cq * 4)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const float4* wp = reinterpret_cast<const float4*>(wk + ((kh * 3 + kw) * CI + cq * 4 + ci) * CO);
+#pragma unroll
+            for (int nq = 0; nq < CO / 4; ++nq) {
+              const float4 wv = wp[nq];
+#pragma unroll
+              for (int p = 0; p < PX; ++p) {
+                const float4 xv4 = xin[p + kw];
+                const float xs = ci == 0 ? xv4.x : (ci == 1 ? xv4.y : (ci == 2 ? xv4.z : xv4.w));
+                acc[p][4 * nq + 0] = fmaf(xs, wv.x, acc[p][4 * nq + 0]);
+                acc[p][4 * nq + 1] = fmaf(xs, wv.y, acc[p][4 * nq + 1]);
+                acc[p][4 * nq + 2] = fmaf(xs, wv.z, acc[p][4 * nq + 2]);
+                acc[p][4 * nq + 3] = fmaf(xs, wv.w, acc[p][4 * nq + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const int wo = w0 + p;
+      if (wo >= Wo) continue;
+      float* op = out + (((long)b * Ho + h) * Wo + wo) * CO;
+#pragma unroll
+      for (int nq = 0; nq < CO / 4; ++nq) {
+        float4 v = make_float4(acc[p][4 * nq], acc[p][4 * nq + 1], acc[p][4 * nq + 2], acc[p][4 * nq + 3]);
+        if (!DGRAD) {
+          if (bias) { v.x += bias[4 * nq]; v.y += bias[4 * nq + 1]; v.z += bias[4 * nq + 2]; v.w += bias[4 * nq + 3]; }
+          v.x = act1(v.x, act); v.y = act1(v.y, act); v.z = act1(v.z, act); v.w = act1(v.w, act);
+        }
+        reinterpret_cast<float4*>(op)[nq] = v;
+      }
+    }
+  }
+}
+
+// thread = (n, channel quad cq, kh); CO = 16 output channels.  Block = 16 * (CI/4) * 3 threads.
+template <int CI>
+__global__ void __launch_bounds__(16 * (CI / 4) * 3) wgrad16_kernel(const float* __restrict__ x,
+                                                                  const float* __restrict__ dy,
+                                                                  float* __restrict__ dw, int B, int H, int W,
+                                                                  int Ho, int Wo, int pad, int rows_per_block) {
+  constexpr int CO = 16;
+  const int n = threadIdx.x % CO, cq = (threadIdx.x / CO) % (CI / 4), kh = threadIdx.x / (CO * (CI / 4));
+  float4 acc[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long rows = (long)B * Ho;
+  const long r0 = (long)blockIdx.x * rows_per_block;
+  const long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  for (long r = r0; r < r1; ++r) {
+    const int ho = (int)(r % Ho), b = (int)(r / Ho);
+    const int hi = ho - pad + kh;
+    if (hi < 0 || hi >= H) continue;                        // uniform per kh group of threads
+    const float* xr = x + (((long)b * H + hi) * W) * CI + cq * 4;
+    const float* gr = dy + (((long)b * Ho + ho) * Wo) * CO + n;
+    // window: x at columns wo-pad, wo-pad+1, wo-pad+2
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, x2 = x0;
+    if (-pad >= 0 && -pad < W) x1 = *reinterpret_cast<const float4*>(xr + (long)(-pad) * CI);
+    if (1 - pad >= 0 && 1 - pad < W) x2 = *reinterpret_cast<const float4*>(xr + (long)(1 - pad) * CI);
+    for (int wo = 0; wo < Wo; ++wo) {
+      x0 = x1; x1 = x2;
+      const int wi = wo + 2 - pad;
+      x2 = (wi >= 0 && wi < W) ? *reinterpret_cast<const float4*>(xr + (long)wi * CI) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float g = gr[(long)wo * CO];
+      acc[0].x = fmaf(g, x0.x, acc[0].x); acc[0].y = fmaf(g, x0.y, acc[0].y);
+      acc[0].z = fmaf(g, x0.z, acc[0].z); acc[0].w = fmaf(g, x0.w, acc[0].w);
+      acc[1].x = fmaf(g, x1.x, acc[1].x); acc[1].y = fmaf(g, x1.y, acc[1].y);
+      acc[1].z = fmaf(g, x1.z, acc[1].z); acc[1].w = fmaf(g, x1.w, acc[1].w);
+      acc[2].x = fmaf(g, x2.x, acc[2].x); acc[2].y = fmaf(g, x2.y, acc[2].y);
+      acc[2].z = fmaf(g, x2.z, acc[2].z); acc[2].w = fmaf(g, x2.w, acc[2].w);
+    }
+  }
+  // dW layout [n][kh][kw][CI]
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) {
+    float* d = dw + (((long)n * 3 + kh) * 3 + kw) * CI + cq * 4;
+    atomicAdd(d + 0, acc[kw].x); atomicAdd(d + 1, acc[kw].y);
+    atomicAdd(d + 2, acc[kw].z); atomicAdd(d + 3, acc[kw].w);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int fd_conv2d_c16_supported(int Cin, int Cout, int KH, int KW, int stride) {
+  return KH == 3 && KW == 3 && stride == 1 && Cout == 16 && (Cin == 16 || Cin == 32);
+}
+
+int fd_conv2d_c16_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                      int pad, int act, void* stream) {
+  FD_REQUIRE(Cin == 16, "fd_conv2d_c16_fwd: Cin must be 16 (Cin = 32 runs on the tensor cores), got %d", Cin);
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  FD_REQUIRE(Ho > 0 && Wo > 0, "fd_conv2d_c16_fwd: empty output");
+  const long tiles = (long)B * Ho * ((Wo + 3) / 4);
+  direct3x3_kernel<16, 16, 4, false><<<min(fd::cdiv(tiles, 128), 148 * 16), 128, 0, (cudaStream_t)stream>>>(
+      x, w, bias, y, B, H, W, Ho, Wo, pad, act);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_conv2d_c16_dgrad(const float* dy, const float* w, float* dx, int B, int H, int W, int Cin, int pad,
+                        void* stream) {
+  FD_REQUIRE(Cin == 16 || Cin == 32, "fd_conv2d_c16_dgrad: Cin must be 16 or 32, got %d", Cin);
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 16) {
+    const long tiles = (long)B * H * ((W + 3) / 4);
+    direct3x3_kernel<16, 16, 4, true><<<min(fd::cdiv(tiles, 128), 148 * 16), 128, 0, st>>>(
+        dy, w, nullptr, dx, B, Ho, Wo, H, W, 2 - pad, 0);
+  } else {
+    const long tiles = (long)B * H * ((W + 1) / 2);
+    direct3x3_kernel<16, 32, 2, true><<<min(fd::cdiv(tiles, 128), 148 * 16), 128, 0, st>>>(
+        dy, w, nullptr, dx, B, Ho, Wo, H, W, 2 - pad, 0);
+  }
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_conv2d_c16_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int pad,
+                        void* stream) {
+  FD_REQUIRE(Cin == 16 || Cin == 32, "fd_conv2d_c16_wgrad: Cin must be 16 or 32, got %d", Cin);
+  const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
+  const long rows = (long)B * Ho;
+  int blocks = (int)(rows < 148 * 2 ? rows : 148 * 2);
+  const int rpb = (int)((rows + blocks - 1) / blocks);
+  blocks = (int)((rows + rpb - 1) / rpb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 16) wgrad16_kernel<16><<<blocks, 16 * 4 * 3, 0, st>>>(x, dy, dw, B, H, W, Ho, Wo, pad, rpb);
+  else wgrad16_kernel<32><<<blocks, 16 * 8 * 3, 0, st>>>(x, dy, dw, B, H, W, Ho, Wo, pad, rpb);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -189,7 +189,14 @@ class Conv2dFn(torch.autograd.Function):
         y = empty_nhwc(B, Cout, Ho, Wo, x.device)
         use_tc = CONV_BACKEND == "tc" and Cin % 32 == 0 and Cout % 16 == 0
         ctx.cout1 = bool(lib.fd_conv2d_cout1_supported(Cin, Cout, KH, KW, stride)) and CONV_BACKEND != "cudacore"
-        if ctx.cout1:
+        ctx.c16 = (bool(lib.fd_conv2d_c16_supported(Cin, Cout, KH, KW, stride)) and CONV_BACKEND == "tc"
+                   and os.environ.get("FD_CONV16", "1") != "0")
+        if ctx.c16 and Cin == 16:
+            # 16 -> 16 channels at full resolution: direct CUDA-core convolution (conv_small.cu)
+            with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
+                _lib.check(lib.fd_conv2d_c16_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, pad, act,
+                                                 _stream()), "fd_conv2d_c16_fwd")
+        elif ctx.cout1:
             # disparity heads: one output channel, streaming kernels (conv_small.cu)
             with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
                 _lib.check(lib.fd_conv2d_cout1_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, pad, act,
@@ -232,19 +239,20 @@ class Conv2dFn(torch.autograd.Function):
                                       act, st), "fd_act_bwd")
             dy = dpre
         dx = None
-        if ctx.cout1:
+        if ctx.cout1 or ctx.c16:
+            dgrad_fn, wgrad_fn, who = ((lib.fd_conv2d_cout1_dgrad, lib.fd_conv2d_cout1_wgrad, "fd_conv2d_cout1")
+                                       if ctx.cout1 else
+                                       (lib.fd_conv2d_c16_dgrad, lib.fd_conv2d_c16_wgrad, "fd_conv2d_c16"))
             if ctx.needs_input_grad[0]:
                 dx = empty_nhwc(B, Cin, H, W, x.device)
                 with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
-                    _lib.check(lib.fd_conv2d_cout1_dgrad(_p(dy), _p(w), _p(dx), B, H, W, Cin, pad, st),
-                               "fd_conv2d_cout1_dgrad")
+                    _lib.check(dgrad_fn(_p(dy), _p(w), _p(dx), B, H, W, Cin, pad, st), who + "_dgrad")
             dw = None
             if ctx.needs_input_grad[1]:
                 dw = ctx.wg if ctx.wg is not None else torch.empty(
                     (Cout, Cin, KH, KW), device=x.device, dtype=torch.float32, memory_format=CL).zero_()
                 with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
-                    _lib.check(lib.fd_conv2d_cout1_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, pad, st),
-                               "fd_conv2d_cout1_wgrad")
+                    _lib.check(wgrad_fn(_p(x), _p(dy), _p(dw), B, H, W, Cin, pad, st), who + "_wgrad")
             return (dx, None if ctx.wg is not None else dw, None if ctx.bg is not None else dbias,
                     None, None, None)
         if ctx.needs_input_grad[0]:

@@ -156,6 +156,17 @@ int fd_conv2d_cout1_dgrad(const float* dy, const float* w, float* dx, int B, int
                           void* stream);
 int fd_conv2d_cout1_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int pad,
                           void* stream);
+/* 16-output-channel 3x3 stride-1 layers with Cin in {16, 32} (DepthDecoder upconv(0,0), upconv(0,1),
+ * reference networks/depth_decoder.py:20-50) as direct convolutions on the CUDA cores; same tensor
+ * conventions as fd_conv2d_*.  fwd takes Cin = 16 only (Cin = 32 forward runs on the tensor cores);
+ * wgrad ADDS into dw [16,3,3,Cin]. */
+int fd_conv2d_c16_supported(int Cin, int Cout, int KH, int KW, int stride);
+int fd_conv2d_c16_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                      int pad, int act, void* stream);
+int fd_conv2d_c16_dgrad(const float* dy, const float* w, float* dx, int B, int H, int W, int Cin, int pad,
+                        void* stream);
+int fd_conv2d_c16_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int pad,
+                        void* stream);
 /* Profiling aid: with FD_TC2_FLAGS bit 7 set, CTA (0,0) of the tensor-core conv kernels writes
  * clock64() stamps of its pipeline roles into this device buffer ((3*256*4 + 8) int64); NULL = off. */
 int fd_debug_set_conv_trace(void* device_buffer);

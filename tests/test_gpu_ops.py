@@ -249,3 +249,30 @@ def test_conv_single_output_channel(cuda, case):
     assert rel_err(xc.grad.cpu(), xr.grad) < 2e-6
     assert rel_err(wc.grad.cpu(), wr.grad) < 1e-5
     assert rel_err(bc.grad.cpu(), br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 16, 26, 42, 0, "elu"), (2, 32, 18, 34, 0, "elu"), (1, 16, 9, 11, 1, "none"),
+                                  (1, 32, 7, 6, 1, "relu")])
+def test_conv_16_output_channels(cuda, case):
+    """DepthDecoder upconv(0,0) 32->16 / upconv(0,1) 16->16 (depth_decoder.py:20-50): direct CUDA-core
+    kernels (forward for Cin = 16, data + weight gradient for both) vs fp64"""
+    from fusiondepth_b200 import ops, _lib
+    B, Cin, H, W, pad, act = case
+    assert _lib.load().fd_conv2d_c16_supported(Cin, 16, 3, 3, 1)
+    x = _rand((B, Cin, H, W), 31)
+    w = _rand((16, Cin, 3, 3), 32, (1.0 / (Cin * 9)) ** 0.5)
+    b = _rand((16,), 33, 0.1)
+    fn = {"elu": F.elu, "relu": F.relu, "none": lambda t: t}[act]
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = fn(F.conv2d(xr, wr, br, 1, pad))
+    gy = _rand(tuple(ref.shape), 34)
+    ref.backward(gy.double())
+    xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    wc = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
+    bc = b.cuda().requires_grad_(True)
+    yc = ops.conv2d(xc, wc, bc, 1, pad, act)
+    yc.backward(gy.cuda())
+    assert rel_err(yc.detach().cpu(), ref.detach()) < 5e-6
+    assert rel_err(xc.grad.cpu(), xr.grad) < 5e-6
+    assert rel_err(wc.grad.cpu(), wr.grad) < 2e-5
+    assert rel_err(bc.grad.cpu(), br.grad) < 2e-5
