@@ -313,18 +313,32 @@ __global__ void __launch_bounds__(16 * (CI / 4) * 3) wgrad16_kernel(const float*
     float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, x2 = x0;
     if (-pad >= 0 && -pad < W) x1 = *reinterpret_cast<const float4*>(xr + (long)(-pad) * CI);
     if (1 - pad >= 0 && 1 - pad < W) x2 = *reinterpret_cast<const float4*>(xr + (long)(1 - pad) * CI);
-    for (int wo = 0; wo < Wo; ++wo) {
-      x0 = x1; x1 = x2;
-      const int wi = wo + 2 - pad;
-      x2 = (wi >= 0 && wi < W) ? *reinterpret_cast<const float4*>(xr + (long)wi * CI) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float g = gr[(long)wo * CO];
+    auto step = [&](const float4& xn, float g) {
+      x0 = x1; x1 = x2; x2 = xn;
       acc[0].x = fmaf(g, x0.x, acc[0].x); acc[0].y = fmaf(g, x0.y, acc[0].y);
       acc[0].z = fmaf(g, x0.z, acc[0].z); acc[0].w = fmaf(g, x0.w, acc[0].w);
       acc[1].x = fmaf(g, x1.x, acc[1].x); acc[1].y = fmaf(g, x1.y, acc[1].y);
       acc[1].z = fmaf(g, x1.z, acc[1].z); acc[1].w = fmaf(g, x1.w, acc[1].w);
       acc[2].x = fmaf(g, x2.x, acc[2].x); acc[2].y = fmaf(g, x2.y, acc[2].y);
       acc[2].z = fmaf(g, x2.z, acc[2].z); acc[2].w = fmaf(g, x2.w, acc[2].w);
+    };
+    auto load_x = [&](int wi) {
+      return (wi >= 0 && wi < W) ? *reinterpret_cast<const float4*>(xr + (long)wi * CI)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    int wo = 0;
+    for (; wo + 4 <= Wo; wo += 4) {            // four independent load pairs in flight per thread
+      float4 xn[4];
+      float g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xn[u] = load_x(wo + u + 2 - pad);
+        g[u] = gr[(long)(wo + u) * CO];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) step(xn[u], g[u]);
     }
+    for (; wo < Wo; ++wo) step(load_x(wo + 2 - pad), gr[(long)wo * CO]);
   }
   // dW layout [n][kh][kw][CI]
 #pragma unroll
@@ -378,7 +392,7 @@ int fd_conv2d_c16_wgrad(const float* x, const float* dy, float* dw, int B, int H
   FD_REQUIRE(Cin == 16 || Cin == 32, "fd_conv2d_c16_wgrad: Cin must be 16 or 32, got %d", Cin);
   const int Ho = H + 2 * pad - 2, Wo = W + 2 * pad - 2;
   const long rows = (long)B * Ho;
-  int blocks = (int)(rows < 148 * 2 ? rows : 148 * 2);
+  int blocks = (int)(rows < 148 * 4 ? rows : 148 * 4);     // ~4 resident blocks per SM hide the load latency
   const int rpb = (int)((rows + blocks - 1) / blocks);
   blocks = (int)((rows + rpb - 1) / rpb);
   cudaStream_t st = (cudaStream_t)stream;

@@ -436,6 +436,10 @@ class TrainStep:
         self.graph.replay()
         return self.loss_out
 
+    def feeder(self) -> "InputFeeder":
+        """Double-buffered host->device input path for the captured step (see InputFeeder)."""
+        return InputFeeder(self)
+
     def _bn_state(self, restore=None):
         bufs = []
         for m in self.models.values():
@@ -444,3 +448,43 @@ class TrainStep:
             return [b.clone() for b in bufs]
         for b, r in zip(bufs, restore):
             b.copy_(r)
+
+
+class InputFeeder:
+    """Host -> device input pipeline for a captured TrainStep (what a DataLoader with pinned memory and
+    prefetch does in the reference's run_epoch, trainer.py:230-236): ``prefetch`` copies the next step's
+    pinned host batch into a device staging set on a copy stream while the current step computes;
+    ``commit`` moves the staging set into the graph's static inputs (device-to-device, a fraction of a
+    millisecond) on the compute stream right before ``replay``."""
+
+    def __init__(self, step: TrainStep):
+        assert step.static_inputs is not None, "capture the step first"
+        self.step = step
+        self.copy_stream = torch.cuda.Stream(device=step.flat.data.device)
+        self.staging_inputs = [{k: torch.empty_like(v) for k, v in b.items()} for b in step.static_inputs]
+        self.staging_noise = [{k: torch.empty_like(v) for k, v in n.items()} for n in step.static_noise]
+        self.ready = torch.cuda.Event()
+        self.consumed = torch.cuda.Event()
+        self.consumed.record(torch.cuda.current_stream())
+
+    def prefetch(self, batches: Sequence[Dict], noises: Sequence[Dict]):
+        self.copy_stream.wait_event(self.consumed)           # staging is no longer being read
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(self.staging_inputs, batches):
+                for k in dst:
+                    dst[k].copy_(src[k], non_blocking=True)
+            for dst, src in zip(self.staging_noise, noises):
+                for k in dst:
+                    dst[k].copy_(src[k], non_blocking=True)
+            self.ready.record(self.copy_stream)
+
+    def commit(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready)
+        for dst, src in zip(self.step.static_inputs, self.staging_inputs):
+            for k in dst:
+                dst[k].copy_(src[k], non_blocking=True)
+        for dst, src in zip(self.step.static_noise, self.staging_noise):
+            for k in dst:
+                dst[k].copy_(src[k], non_blocking=True)
+        self.consumed.record(cur)
