@@ -33,6 +33,8 @@ NUM_LAYERS = 18
 METRIC = "training images/sec (640x192 b12)"
 CONV_GFLOP_PER_IMAGE = 182.4            # fwd+bwd, BASELINE.md section 4
 LOSS_BYTES_PER_IMAGE = 431.8 * H * W    # fwd+bwd algorithmic bytes, SURVEY.md section 8(d)
+WORKLOAD = ("trainer.py step (enc/dec/pose fwd+bwd + reprojection loss + Adam), "
+            "ResNet-18, 640x192, batch 12 per GPU = 2 micro-batches of 6")
 
 
 def peaks():
@@ -150,7 +152,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": 0,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "trainer.py step, ResNet-18, 640x192, batch 12 (2 x 6), host CPU"},
+        "config": {"workload": WORKLOAD, "cuda_graph": False, "parallelism": "host cpu, %d threads" % cores,
+                   "l2": "n/a (host)"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -406,8 +409,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "trainer.py step (enc/dec/pose fwd+bwd + reprojection loss + Adam), "
-                                   "ResNet-18, 640x192, batch 12 per GPU = 2 micro-batches of 6",
+            "config": {"workload": WORKLOAD,
                        "cuda_graph": not args.no_graph, "parallelism": "dp%d" % world,
                        "l2": "no explicit flush: each step streams >2 GB of activations (>> 126 MB L2)"},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
