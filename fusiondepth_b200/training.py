@@ -412,7 +412,9 @@ class TrainStep:
         s = self.stream
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):
+            # at least one eager pass: allocator warm-up, NCCL, and the one-time host->device tables
+            # (FlatParams.prepare_weights) must not happen under capture
+            for _ in range(max(int(warmup), 1)):
                 self._run(self.static_inputs, self.static_noise)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
