@@ -173,3 +173,32 @@ def test_cuda_graph_replay_matches_eager(cuda):
     # weight gradients are accumulated with fp32 atomics (order varies run to run) and the first
     # Adam step moves every weight by ~lr * sign(g): compare within a few lr
     assert float((w_graph - step.flat.data).abs().max()) <= 3.0 * step.lr
+
+
+def test_abs_rel_matches_reference_disparities(cuda):
+    """evaluate_depth.py's AbsRel (evaluate_depth.py:42-60, 344-378: bilinear resize to the ground-truth
+    size, Garg crop, per-image median scaling, clip to [1e-3, 80]) of OUR eval-mode disparities against
+    the AbsRel of the reference's disparities (fixture) on the same synthetic sparse ground truth:
+    within 1e-4 (BASELINE.json north_star)."""
+    from fusiondepth_b200 import networks
+    from fusiondepth_b200.layers import disp_to_depth
+    g = np.load(GOLDEN + "/forward_variants.npz")
+    rgb, two = torch.from_numpy(g["rgb"]).cuda(), torch.from_numpy(g["two"]).cuda()
+    enc = networks.ResnetEncoder(18, False)
+    benc = networks.ResnetEncoder(18, False, beam_encoder=True)
+    dec = networks.DepthDecoder(enc.num_ch_enc, [0, 1, 2, 3])
+    for i, m in enumerate((enc, benc, dec)):
+        m.load_state_dict(synth_weights(m.state_dict(), 1000 + 18 * 10 + i))
+        m.cuda().eval()
+    with torch.no_grad():
+        ours = dec(list(enc(rgb)), beam_features=benc(two))[("disp", 0)]
+    ref = torch.from_numpy(g["r18/disp0"])
+    assert ours.shape == ref.shape
+    rng = np.random.RandomState(7)
+    for b in range(ours.shape[0]):
+        gt_h, gt_w = 2 * ours.shape[2] - 9, 2 * ours.shape[3] - 38          # KITTI-like odd size, upscaling
+        gt = rng.uniform(2.0, 60.0, (gt_h, gt_w)).astype(np.float32)
+        gt[rng.uniform(size=gt.shape) < 0.7] = 0.0                             # sparse LiDAR ground truth
+        a_ours = SO.eval_abs_rel(disp_to_depth(ours[b, 0].cpu(), 0.1, 100.0)[0].numpy(), gt)
+        a_ref = SO.eval_abs_rel(disp_to_depth(ref[b, 0], 0.1, 100.0)[0].numpy(), gt)
+        assert abs(a_ours - a_ref) < 1e-4, (b, a_ours, a_ref)
