@@ -411,17 +411,15 @@ int launch_tc2(const TcArgs& a, cudaStream_t st) {
 
 template <int MODE>
 int dispatch_tc2(const TcArgs& a, cudaStream_t st) {
-  // Tile width: the widest BN dividing N, except that 128-wide layers with few pixel tiles run as
-  // 64-wide tiles (twice the CTAs for the 148 SMs, and four main accumulators instead of two).
-  FD_REQUIRE((((uintptr_t)a.w | (uintptr_t)a.wlo | (uintptr_t)a.x) & 15) == 0,
-             "conv_tc2: operands must be 16-byte aligned");
-  FD_REQUIRE(a.M < (1L << 31) && a.KH <= 8 && a.KW <= 8, "conv_tc2: problem too large (M=%ld, %dx%d)", a.M,
-             a.KH, a.KW);
-  FD_REQUIRE((long)a.B * a.Hg * a.Wg * a.Cg < (1L << 31), "conv_tc2: gathered tensor has 2^31 or more elements");
-  static int narrow_below = -1;        // FD_TC2_NARROW: CTA-count threshold below which N=128 layers use N=64 tiles
+  // Tile width: the widest BN dividing N.  Splitting the few-pixel N >= 128 layers (layer3 / layer4,
+  // 24-46 CTAs) into 64-wide tiles lowers their latency alone but costs ~1.5x the SM-time (every extra
+  // N tile repeats the A gather and split); inside the captured step, where the other streams keep the
+  // SMs full, the wide tiles win (368.8 vs 351.7 images/s).  FD_TC2_NARROW=<ctas> restores the split for
+  // layers with fewer CTAs than that.
+  static int narrow_below = -1;
   if (narrow_below < 0) {
     const char* e = getenv("FD_TC2_NARROW");
-    narrow_below = e ? atoi(e) : 64;
+    narrow_below = e ? atoi(e) : 0;
   }
   int bn = a.N % 128 == 0 ? 128 : (a.N % 64 == 0 ? 64 : (a.N % 32 == 0 ? 32 : 16));
   if (bn == 128 && fd::cdiv(a.M, BM) * (a.N / 128) < narrow_below) bn = 64;
