@@ -411,6 +411,11 @@ int launch_tc2(const TcArgs& a, cudaStream_t st) {
 
 template <int MODE>
 int dispatch_tc2(const TcArgs& a, cudaStream_t st) {
+  FD_REQUIRE((((uintptr_t)a.w | (uintptr_t)a.wlo | (uintptr_t)a.x) & 15) == 0,
+             "conv_tc2: operands must be 16-byte aligned");
+  FD_REQUIRE(a.M < (1L << 31) && a.KH <= 8 && a.KW <= 8, "conv_tc2: problem too large (M=%ld, %dx%d)", a.M,
+             a.KH, a.KW);
+  FD_REQUIRE((long)a.B * a.Hg * a.Wg * a.Cg < (1L << 31), "conv_tc2: gathered tensor has 2^31 or more elements");
   // Tile width: the widest BN dividing N.  Splitting the few-pixel N >= 128 layers (layer3 / layer4,
   // 24-46 CTAs) into 64-wide tiles lowers their latency alone but costs ~1.5x the SM-time (every extra
   // N tile repeats the A gather and split); inside the captured step, where the other streams keep the
