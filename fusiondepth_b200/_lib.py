@@ -68,6 +68,7 @@ _SIGNATURES = {
     "fd_weight_transpose_split": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
     "fd_weight_transpose_split_batched": (c_int, [_P, _P, _P, _P, _I, _L, _P]),
     "fd_conv2d_fwd_tc": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_conv2d_fwd_tc_stats": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "fd_conv2d_dgrad_tc": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_wgrad_tc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fd_act_bwd": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P]),
@@ -80,7 +81,7 @@ _SIGNATURES = {
     "fd_conv2d_c16_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_c16_dgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_c16_wgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "fd_bn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P, _L, _I, _F, _P]),
+    "fd_bn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "fd_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "fd_maxpool3x3s2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_maxpool3x3s2_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -704,12 +704,26 @@ int fd_weight_transpose_split_batched(const float* flat, float* flat_t, float* f
   return 0;
 }
 
+int fd_conv2d_fwd_tc_stats(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           int act, double* stats, void* stream);
+
 int fd_conv2d_fwd_tc(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
                      int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                      int act, void* stream) {
+  return fd_conv2d_fwd_tc_stats(x, w, w_lo, bias, y, B, H, W, Cin, Cout, KH, KW, stride, pad, act, nullptr,
+                                stream);
+}
+
+int fd_conv2d_fwd_tc_stats(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           int act, double* stats, void* stream) {
   FD_REQUIRE(fd_conv2d_tc_supported(Cin, Cout),
              "fd_conv2d_fwd_tc: needs Cin %% 32 == 0 and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
+  FD_REQUIRE(stats == nullptr || (tc_use_v2() && bias == nullptr && act == FD_ACT_NONE),
+             "fd_conv2d_fwd_tc_stats: channel statistics need the conv_tc2 kernels, no bias and no activation");
   TcArgs a;
+  a.stats = stats;
   a.x = x; a.w = w; a.wlo = w_lo; a.bias = bias; a.y = y;
   a.B = B; a.Hg = H; a.Wg = W; a.Cg = Cin;
   a.Ho = (H + 2 * pad - KH) / stride + 1;
@@ -727,6 +741,7 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
   FD_REQUIRE(fd_conv2d_tc_supported(Cout, Cin),
              "fd_conv2d_dgrad_tc: needs Cout %% 32 == 0 and Cin %% 16 == 0 (got %d, %d)", Cout, Cin);
   TcArgs a;
+  a.stats = nullptr;
   a.x = dy; a.w = wt; a.wlo = wt_lo; a.bias = nullptr; a.y = dx;
   a.B = B;
   a.Hg = (H + 2 * pad - KH) / stride + 1;

@@ -52,7 +52,7 @@ struct Cfg2 {
   static constexpr bool PAIR = BN <= 64;
   static constexpr int NMAIN_ = PAIR ? (512 - ACC0 - BN) / (2 * BN) : (512 - ACC0) / BN - 1;
   static constexpr int NMAIN = NMAIN_ > 7 ? 7 : NMAIN_;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row table*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row table*/ + 1024 /*CTA channel sums*/;
 };
 
 template <int BN, int MODE>
@@ -84,6 +84,9 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   // One row per loader thread, published through shared memory by the prologue barrier -- not eight
   // rows of integer divisions per thread in front of the first load (measured: 6.7k cycles per CTA).
   const uint32_t tab_ptr = bars + 512u, tab_mask = tab_ptr + 4u * BM;
+  const uint32_t cta_sums = tab_mask + 4u * BM;            // [2][BN] floats, only with a.stats
+  if (a.stats && tid >= BM && tid < BM + 2 * BN)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(tid - BM)), "f"(0.f) : "memory");
   if (tid < BM) {
     const long m = m0 + tid;
     int eoff = 0;                      // element offset of the pixel's first gathered channel (may be < 0)
@@ -292,6 +295,31 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           }
         }
       }
+      if (a.stats) {
+        // Per-channel sum / sum of squares of this warp's 32 rows (rows past M are exact zeros):
+        // transpose-reduce, 16 shuffles per statistic; even lanes end up owning one channel each.
+        float s1[16], s2[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { s1[e] = acc[e]; s2[e] = acc[e] * acc[e]; }
+#pragma unroll
+        for (int width = 8, off = 16; width >= 1; width >>= 1, off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < width; ++i) {
+            const float send1 = up ? s1[i] : s1[i + width], send2 = up ? s2[i] : s2[i + width];
+            const float keep1 = up ? s1[i + width] : s1[i], keep2 = up ? s2[i + width] : s2[i];
+            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+          }
+        }
+        s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+        if (!(lane & 1)) {
+          const int ch = c + ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)ch), "f"(s1[0]) : "memory");
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(BN + ch)), "f"(s2[0]) : "memory");
+        }
+      }
       if (m < a.M && n0 + c < a.N) {
         float o[16];
 #pragma unroll
@@ -302,6 +330,17 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         float4* dst = reinterpret_cast<float4*>(a.y + m * a.N + n0 + c);
 #pragma unroll
         for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+      }
+    }
+    if (a.stats) {
+      // the eight epilogue warps meet, then 2*BN threads fold the CTA's sums into the fp64 totals
+      asm volatile("bar.sync 1, %0;" ::"n"(NSPLIT2) : "memory");
+      const int i = tid - NLOAD2;
+      if (i < 2 * BN) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cta_sums + 4u * (uint32_t)i));
+        const int stat = i / BN, ch = n0 + (i - stat * BN);
+        if (ch < a.N) atomicAdd(a.stats + (long)stat * a.N + ch, (double)v);
       }
     }
   } else if (warp == TMA_WARP2) {

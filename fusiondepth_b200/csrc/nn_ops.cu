@@ -805,9 +805,9 @@ int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long 
 int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
               float* running_mean, float* running_var, int training, float momentum, float eps,
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
-              float stat_weight, void* stream) {
+              float stat_weight, int stats_ready, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn_fused_ok(M, C)) {
+  if (!stats_ready && bn_fused_ok(M, C)) {
     bn_fwd_fused_kernel<<<C / BNF_CG, 256, BNF_SMEM, st>>>(x, residual, gamma, beta, running_mean, running_var,
                                                           training, momentum, eps, stat_weight, save_mean,
                                                           save_rstd, relu, y, (int)M, C);
@@ -817,7 +817,7 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
   const int vec = (C % 4 == 0) ? 4 : 1;
   BnGeom g = bn_geom(M, C, vec);
   const size_t sm = sizeof(double) * 2 * vec * 256;
-  if (training) {
+  if (training && !stats_ready) {       // stats_ready: ws already holds the sums (fd_conv2d_fwd_tc_stats)
     BnGeom gr = bn_geom(M, C, vec, true);
     cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
     if (vec == 4) bn_stats_kernel<4><<<gr.grid, gr.block, sm, st>>>(x, ws, M, C);

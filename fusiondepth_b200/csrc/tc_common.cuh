@@ -18,6 +18,7 @@ struct TcArgs {
   long M;
   int K;
   int flags;          // conv_tc2: bit 0 = loader signals `landed` per warp through cp.async groups
+  double* stats;      // conv_tc2 forward, optional: [2][N] per-channel sum / sum of squares of y (+=)
 };
 // conv_tc2.cu: A-operand-in-TMEM kernels (mode 0 forward, 1 data gradient)
 int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st);

@@ -26,14 +26,14 @@ class Conv2d(nn.Conv2d):
         super(Conv2d, self).__init__(*a, **k)
         self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
 
-    def forward(self, x, act="none"):
-        return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], act)
+    def forward(self, x, act="none", stats=None):
+        return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], act, stats)
 
 
 class BatchNorm2d(nn.BatchNorm2d):
     """nn.BatchNorm2d state, forward on fd_bn_* with optional fused residual add and ReLU."""
 
-    def forward(self, x, residual=None, relu=False):
+    def forward(self, x, residual=None, relu=False, stats=None):
         training = self.training or not self.track_running_stats
         stat_weight = -1.0
         if self.training and self.track_running_stats:
@@ -43,12 +43,22 @@ class BatchNorm2d(nn.BatchNorm2d):
             if stat_weight < 0:
                 self.num_batches_tracked += 1
         return ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var,
-                              residual, training, self.momentum, self.eps, relu, stat_weight)
+                              residual, training, self.momentum, self.eps, relu, stat_weight, stats)
+
+
+def conv_bn(conv, bn, x, residual=None, relu=False):
+    """bn(conv(x)) (+ residual, ReLU).  With ops.FUSE_BN_STATS the batch statistics come out of the
+    convolution's epilogue (a zeroed fp64 [2*C] buffer travels from the conv to the BatchNorm)."""
+    ws = None
+    if (bn.training or not bn.track_running_stats) and ops.conv_emits_stats(
+            conv.in_channels, conv.out_channels, conv.bias is not None):
+        ws = torch.zeros(2 * conv.out_channels, device=x.device, dtype=torch.float64)
+    return bn(conv(x, stats=ws), residual=residual, relu=relu, stats=ws)
 
 
 class _Downsample(nn.Sequential):
     def forward(self, x):
-        return self[1](self[0](x))
+        return conv_bn(self[0], self[1], x)
 
 
 class BasicBlock(nn.Module):
@@ -65,9 +75,9 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = self.bn1(self.conv1(x), relu=True)
+        out = conv_bn(self.conv1, self.bn1, x, relu=True)
         identity = x if self.downsample is None else self.downsample(x)
-        return self.bn2(self.conv2(out), residual=identity, relu=True)
+        return conv_bn(self.conv2, self.bn2, out, residual=identity, relu=True)
 
 
 class Bottleneck(nn.Module):
@@ -86,10 +96,10 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = self.bn1(self.conv1(x), relu=True)
-        out = self.bn2(self.conv2(out), relu=True)
+        out = conv_bn(self.conv1, self.bn1, x, relu=True)
+        out = conv_bn(self.conv2, self.bn2, out, relu=True)
         identity = x if self.downsample is None else self.downsample(x)
-        return self.bn3(self.conv3(out), residual=identity, relu=True)
+        return conv_bn(self.conv3, self.bn3, out, residual=identity, relu=True)
 
 
 class ResNetTrunk(nn.Module):

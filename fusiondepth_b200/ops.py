@@ -173,9 +173,20 @@ def prep_input(x):
 
 
 # --------------------------------------------------------------------------------------------
+# Experimental (FD_BN_FUSE_STATS=1, not yet validated on hardware): BatchNorm batch statistics out of the
+# tensor-core convolution epilogue instead of a separate pass over the conv output.
+FUSE_BN_STATS = os.environ.get("FD_BN_FUSE_STATS", "0") == "1"
+
+
+def conv_emits_stats(Cin, Cout, has_bias) -> bool:
+    """True when conv2d(..., stats=ws) will fill `ws` (tensor-core conv_tc2 forward path)."""
+    return (FUSE_BN_STATS and CONV_BACKEND == "tc" and not has_bias and Cin % 32 == 0 and Cout % 16 == 0
+            and os.environ.get("FD_CONV_TC", "") != "v1" and not (Cout == 16 and Cin == 16))
+
+
 class Conv2dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, act):
+    def forward(ctx, x, weight, bias, stride, pad, act, stats=None):
         _require_cuda(x, "conv2d")
         lib = _lib.load()
         x = nhwc(x)
@@ -208,13 +219,16 @@ class Conv2dFn(torch.autograd.Function):
                 return (t,)
             (wlo,) = _cached((w.data_ptr(), "lo"), make_lo)
             with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
-                _lib.check(lib.fd_conv2d_fwd_tc(_p(x), _p(w), _p(wlo), _p(bias), _p(y), B, H, W, Cin,
-                                                Cout, KH, KW, stride, pad, act, _stream()),
+                _lib.check(lib.fd_conv2d_fwd_tc_stats(_p(x), _p(w), _p(wlo), _p(bias), _p(y), B, H, W, Cin,
+                                                      Cout, KH, KW, stride, pad, act, _p(stats), _stream()),
                            "fd_conv2d_fwd_tc")
+            stats = None
         else:
             with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
                 _lib.check(lib.fd_conv2d_fwd(_p(x), _p(w), _p(bias), _p(y), B, H, W, Cin, Cout, KH, KW,
                                              stride, pad, act, _stream()), "fd_conv2d_fwd")
+        if stats is not None:
+            raise RuntimeError("conv2d: channel statistics were requested on a path that does not produce them")
         ctx.save_for_backward(x, w, y if act != 0 else None)
         ctx.cfg = (stride, pad, act, bias is not None)
         ctx.wg, ctx.bg = _direct_grad(weight), _direct_grad(bias)
@@ -254,7 +268,7 @@ class Conv2dFn(torch.autograd.Function):
                 with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
                     _lib.check(wgrad_fn(_p(x), _p(dy), _p(dw), B, H, W, Cin, pad, st), who + "_wgrad")
             return (dx, None if ctx.wg is not None else dw, None if ctx.bg is not None else dbias,
-                    None, None, None)
+                    None, None, None, None)
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(B, Cin, H, W, x.device)
             if CONV_BACKEND == "tc" and Cout % 32 == 0 and Cin % 16 == 0:
@@ -288,11 +302,13 @@ class Conv2dFn(torch.autograd.Function):
                                                    stride, pad, st), "fd_conv2d_wgrad")
         # gradients written straight into the parameters' buffers are not handed back to autograd
         return (dx, None if ctx.wg is not None else dw, None if ctx.bg is not None else dbias,
-                None, None, None)
+                None, None, None, None)
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, act="none"):
-    return Conv2dFn.apply(x, weight, bias, int(stride), int(pad), ACT[act])
+def conv2d(x, weight, bias=None, stride=1, pad=0, act="none", stats=None):
+    """stats: optional zeroed float64 [2*Cout] tensor that receives the per-channel sum / sum of squares
+    of the output (only on the path conv_emits_stats() describes)."""
+    return Conv2dFn.apply(x, weight, bias, int(stride), int(pad), ACT[act], stats)
 
 
 # --------------------------------------------------------------------------------------------
@@ -366,7 +382,7 @@ def stem_conv(x, weight):
 class BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps,
-                relu, stat_weight):
+                relu, stat_weight, stats=None):
         _require_cuda(x, "batch_norm")
         lib = _lib.load()
         x = nhwc(x)
@@ -377,10 +393,11 @@ class BatchNormFn(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(C, device=x.device, dtype=torch.float32)
         rstd = torch.empty(C, device=x.device, dtype=torch.float32)
-        ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        ws = stats if stats is not None else torch.empty(2 * C, device=x.device, dtype=torch.float64)
         _lib.check(lib.fd_bn_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(running_mean),
                                  _p(running_var), int(training), momentum, eps, int(relu), _p(y),
-                                 _p(mean), _p(rstd), _p(ws), M, C, stat_weight, _stream()), "fd_bn_fwd")
+                                 _p(mean), _p(rstd), _p(ws), M, C, stat_weight, int(stats is not None),
+                                 _stream()), "fd_bn_fwd")
         ctx.save_for_backward(x, y, gamma, mean, rstd)
         ctx.cfg = (int(relu), int(training), residual is not None)
         ctx.gg, ctx.gb = _direct_grad(gamma), _direct_grad(beta)
@@ -404,14 +421,16 @@ class BatchNormFn(torch.autograd.Function):
                                  _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, int(direct),
                                  _stream()), "fd_bn_bwd")
         if direct:
-            return dx, None, None, None, None, dres, None, None, None, None, None
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+            return dx, None, None, None, None, dres, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
 
 
 def batch_norm(x, gamma, beta, running_mean, running_var, residual=None, training=True,
-               momentum=0.1, eps=1e-5, relu=False, stat_weight=-1.0):
+               momentum=0.1, eps=1e-5, relu=False, stat_weight=-1.0, stats=None):
+    """stats: float64 [2*C] sums already produced by conv2d(..., stats=...) for this x (training only)."""
     return BatchNormFn.apply(x, gamma, beta, running_mean, running_var, residual, bool(training),
-                             float(momentum), float(eps), bool(relu), float(stat_weight))
+                             float(momentum), float(eps), bool(relu), float(stat_weight),
+                             stats if training else None)
 
 
 # --------------------------------------------------------------------------------------------

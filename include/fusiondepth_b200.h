@@ -130,6 +130,12 @@ int fd_weight_transpose(const float* w, float* wt, int Cout, int taps, int Cin, 
  * (fd_tf32_split); for the data gradient wt / wt_lo come from fd_weight_transpose_split. */
 int fd_conv2d_tc_supported(int gathered_channels, int produced_channels);
 int fd_tf32_split(const float* w, float* w_lo, long n, void* stream);
+/* fd_conv2d_fwd_tc that also adds the per-channel sum and sum of squares of y into stats [2][Cout] (fp64,
+ * zeroed by the caller): the BatchNorm batch statistics come out of the convolution epilogue (no bias,
+ * no activation; stats may be NULL). */
+int fd_conv2d_fwd_tc_stats(const float* x, const float* w, const float* w_lo, const float* bias, float* y,
+                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                           int act, double* stats, void* stream);
 /* ... for every conv weight of a flat parameter buffer in ONE launch: desc (device, int64 [n][5]) rows are
  * {first element of tensor j in the concatenated index space, offset of tensor j in the flat buffers,
  *  Cout, taps, Cin}; the transposed tensors land at the same offsets of flat_t / flat_tlo. */
@@ -180,11 +186,13 @@ int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long 
  * stat_weight < 0: running = (1-momentum)*running + momentum*stat (nn.BatchNorm2d).  stat_weight >= 0:
  * running += stat_weight*stat with atomics -- for calls of one layer that run concurrently inside an
  * optimiser step, after the caller has decayed the buffers by (1-momentum)^n_calls once.
+ * stats_ready != 0: ws already holds the per-channel sum / sum of squares of x (written by
+ * fd_conv2d_fwd_tc_stats into a zeroed buffer); the statistics pass over x is skipped.
  * accumulate_param_grads: dgamma/dbeta are added (atomically) into existing buffers instead of set. */
 int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
               float* running_mean, float* running_var, int training, float momentum, float eps,
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
-              float stat_weight, void* stream);
+              float stat_weight, int stats_ready, void* stream);
 int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
               const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
               float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
