@@ -149,7 +149,7 @@ def run_reference(args):
     value = MICRO_B / (ms / 1e3)
     sample = "1 micro-batch of %d images (fwd+bwd+Adam) per step, oracle port, fp32" % MICRO_B
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": 0,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "cuda_graph": False, "parallelism": "host cpu, %d threads" % cores,
