@@ -25,6 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The captured step has up to 14 concurrent branches (2 micro-batches x (1 + 5 trunk streams) + copies);
+# the default 8 hardware work queues alias them (measured +3 % with 32, the maximum).  Must be set before
+# the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -411,6 +416,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "cuda_graph": not args.no_graph, "parallelism": "dp%d" % world,
+                       "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                        "l2": "no explicit flush: each step streams >2 GB of activations (>> 126 MB L2)"},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
