@@ -209,27 +209,32 @@ def dominant_kernel_leg(dev):
             "achieved_tflops": flop / (us * 1e-6) / 1e12, "mma_tflops_issued": 3 * flop / (us * 1e-6) / 1e12}
 
 
-def cpu_baseline_leg():
+def cpu_baseline_leg(sds0, batches, noises):
     """Bounded CPU sample on rank 0: one optimiser step (2 micro-batches of 6) after one warm-up
-    micro-batch, through the oracle port."""
+    micro-batch, through the oracle port -- on the SAME initial weights and the SAME batch as the CUDA
+    arm's first step, so the oracle's loss for that step is the parity reference for `loss_first`."""
     from oracle import step_oracle as SO
-    from fusiondepth_b200 import training
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    models = training.build_models(NUM_LAYERS, "cpu")
-    sds = {name: {k: (v.detach().clone().contiguous().requires_grad_(True)
-                      if v.is_floating_point() and "running" not in k else v.detach().clone())
-                  for k, v in m.state_dict().items()} for name, m in models.items()}
-    batches, noises = synthetic_step_inputs(2)
-    _, l = SO.process_batch(sds, batches[0], noises[0], NUM_LAYERS, True)
+
+    def fresh():
+        return {name: {k: (v.detach().clone().contiguous().requires_grad_(True)
+                           if v.is_floating_point() and "running" not in k else v.detach().clone())
+                       for k, v in sd.items()} for name, sd in sds0.items()}
+    warm = fresh()
+    _, l = SO.process_batch(warm, batches[0], noises[0], NUM_LAYERS, True)
     (l["loss"] / ACCUM).backward()
+    sds = fresh()
     t0 = time.perf_counter()
+    total = 0.0
     for b, n in zip(batches, noises):
         _, l = SO.process_batch(sds, b, n, NUM_LAYERS, True)
         (l["loss"] / ACCUM).backward()
+        total += float(l["loss"]) / ACCUM
     dt = time.perf_counter() - t0
     return {"value": MICRO_B * ACCUM / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "1 optimiser step (2 micro-batches of 6, fwd+bwd) after 1 warm-up micro-batch"}
+            "sample": "1 optimiser step (2 micro-batches of 6, fwd+bwd) after 1 warm-up micro-batch",
+            "oracle_loss_first_step": total}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -254,6 +259,10 @@ def run_ours(args):
     _phase("process group up")
     torch.manual_seed(0)                          # same initial weights on every rank
     models = training.build_models(NUM_LAYERS, dev)
+    sds0 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sds0 = {name: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+                for name, m in models.items()}
     step = training.TrainStep(models, lr=1e-4 * (MICRO_B * ACCUM) / 8, accumulate=ACCUM)
     cpu_batches, cpu_noises = synthetic_step_inputs(100 + rank, dev)
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in cpu_batches]
@@ -280,9 +289,10 @@ def run_ours(args):
         return
 
     n0 = _lib.launch_count()
+    first_loss = None
     if args.no_graph:
         run = lambda: step.step(batches, noises)
-        run()
+        first_loss = float(run())
         launches_per_step = _lib.launch_count() - n0
     else:
         step.capture(batches, noises, warmup=1)
@@ -303,7 +313,10 @@ def run_ours(args):
         return float(t) / k, out
 
     _phase("captured / first step done, launches/step=%d" % launches_per_step)
-    first_loss = float(run())
+    if first_loss is None:
+        first_loss = float(run())               # the captured step starts from the initial weights
+    else:
+        run()
     _phase("first replay done")
     for _ in range(max(args.warmup, 3) - 1):
         run()
@@ -427,11 +440,26 @@ def run_ours(args):
             "clocks": clocks, "roofline": roofline, "roofline_loss": roofline_loss,
             "loss_first": first_loss, "loss": float(loss),
         }
+        parity_ok = True
         if world == 1 and not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_baseline_leg()
+            cb = cpu_baseline_leg(sds0, cpu_batches, cpu_noises)
+            want = cb.pop("oracle_loss_first_step")
+            rel = abs(first_loss - want) / abs(want)
+            parity_ok = rel < 1e-4
+            result["cpu_baseline"] = cb
+            result["parity"] = {"what": "loss of the first optimiser step (12 images, initial weights): CUDA "
+                                        "path vs the CPU oracle on the identical batch",
+                                "loss_first": first_loss, "oracle_loss": want, "rel_err": rel, "tol": 1e-4,
+                                "ok": parity_ok}
     if result is not None:
         print(json.dumps(result))
         sys.stdout.flush()
+        if not parity_ok:
+            sys.stderr.write("bench.py: PARITY FAILURE: loss_first %.9g vs oracle %.9g (rel %.3g > 1e-4)\n"
+                             % (first_loss, want, rel))
+            sys.stderr.flush()
+            if world == 1:
+                sys.exit(3)
     if world > 1:
         # A communicator that is referenced by a captured CUDA graph does not tear down cleanly
         # (destroy_process_group blocks); the line is out, so leave without the NCCL teardown.

@@ -31,7 +31,8 @@ class PhotolossDesc(ctypes.Structure):
         ("min_depth", c_float), ("max_depth", c_float),
         ("smoothness", c_float),
         ("si_thresh", c_float), ("si_var", c_float),
-        ("use_si", c_int),
+        ("si_scales", c_int),
+        ("si_pred_mul", c_float), ("si_tgt_mul", c_float), ("si_lo", c_float), ("si_weight", c_float),
         ("sel", c_void_p),
         ("out_depth", c_void_p * 4),
         ("out_color", (c_void_p * 2) * 4),
@@ -56,6 +57,24 @@ _SIGNATURES = {
     "fd_photoloss_workspace_bytes": (c_size_t, [_I, _I, _I]),
     "fd_photoloss_fwd": (c_int, [POINTER(PhotolossDesc), _P, _P, _P]),
     "fd_photoloss_bwd": (c_int, [POINTER(PhotolossDesc), _P, POINTER(c_void_p * 4), _P, _P, _P, _P]),
+    "fd_upsample_bilinear_fwd": (c_int, [_P, _P, _L, _I, _I, _I, _I, _P]),
+    "fd_upsample_bilinear_bwd": (c_int, [_P, _P, _L, _I, _I, _I, _I, _P]),
+    "fd_backproject_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "fd_backproject_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "fd_project3d_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "fd_project3d_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P]),
+    "fd_grid_sample_border_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_grid_sample_border_bwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fd_pose_matrix_fwd": (c_int, [_P, _P, _I, _P, _I, _P]),
+    "fd_pose_matrix_bwd": (c_int, [_P, _P, _I, _P, _P, _P, _I, _P]),
+    "fd_cat_xy": (c_int, [_P, _P, _P, _I, _I, _I, _P]),
+    "fd_ssim_fwd": (c_int, [_P, _P, _P, _L, _I, _I, _P]),
+    "fd_ssim_bwd": (c_int, [_P, _P, _P, _P, _L, _I, _I, _P, _P]),
+    "fd_refine_pack_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "fd_refine_pack": (c_int, [_P, _P, _P, POINTER(c_void_p * 4), _I, _I, _I, _I, _I, _I, _I, _F, _F,
+                               POINTER(c_void_p * 4), _P, _P, _P]),
+    "fd_masked_median_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "fd_masked_median": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
     "fd_prep_input": (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
     "fd_stem_im2col": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "fd_pad_rows": (c_int, [_P, _P, _I, _I, _I, _I, _P]),

@@ -274,15 +274,18 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       float acc[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-      // list of accumulator column bases: PAIR: main_0, corr2_0, main_1, ... then corr1; else main_i, corr
-      const int nacc = C::PAIR ? 2 * nmain + 1 : nmain + 1;
+      // list of accumulator column bases: PAIR: main_0, corr2_0, main_1, ... then corr1; else main_i, corr.
+      // Single-pass TF32 (flags bit 11, FD_CONV_PRECISION=tf32): only the main accumulators exist.
+      const bool single = (a.flags & 0x800) != 0;
+      const int nacc = single ? nmain : (C::PAIR ? 2 * nmain + 1 : nmain + 1);
       for (int g = 0; g < nacc; g += 4) {
         uint32_t v[4][16];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = g + u;
           if (i < nacc) {
-            const int col = i == nacc - 1 ? 0 : (C::PAIR ? BN + i * BN : (1 + i) * BN);
+            const int col = single ? (C::PAIR ? BN + 2 * i * BN : (1 + i) * BN)
+                                   : (i == nacc - 1 ? 0 : (C::PAIR ? BN + i * BN : (1 + i) * BN));
             tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);
           }
         }
@@ -380,7 +383,13 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       if (elect_one()) {
         const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
         const uint32_t ta = tmem_base + (uint32_t)(t * 64), tal = ta + 32u;
-        if (C::PAIR) {
+        if (a.flags & 0x800) {
+          // single-pass TF32: D += tf32(A) * tf32(W), nothing else (what cuDNN computes with allow_tf32)
+          const uint32_t d_main = d_corr + (uint32_t)(C::PAIR ? BN + (kb % C::NMAIN) * 2 * BN : (1 + kb % C::NMAIN) * BN);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32_ts(d_main, ta + 8u * k, db + (uint64_t)(k * 32 >> 4), idesc, (kb >= C::NMAIN) || (k != 0));
+        } else if (C::PAIR) {
           const uint32_t d_pair = d_corr + (uint32_t)(BN + (kb % C::NMAIN) * 2 * BN);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {

@@ -722,10 +722,12 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, float* __re
 }
 
 // state[0] = step (int bits), state[1] = lr / (1 - beta1^t), state[2] = sqrt(1 - beta2^t);
-// kept on the device so a captured CUDA graph advances the step on every replay
+// kept on the device so a captured CUDA graph advances the step on every replay.  lr < 0: the learning
+// rate is the float in state[3] (written by the host between replays: StepLR, trainer.py:131-132, 266).
 __global__ void adam_scalars_kernel(int* state, float lr, float beta1, float beta2) {
   int t = state[0] + 1;
   state[0] = t;
+  if (lr < 0.f) lr = ((float*)state)[3];
   double bc1 = 1.0 - pow((double)beta1, (double)t);
   double bc2 = 1.0 - pow((double)beta2, (double)t);
   ((float*)state)[1] = (float)((double)lr / bc1);

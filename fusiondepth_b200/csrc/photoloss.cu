@@ -43,7 +43,8 @@ struct PLArgs {
   float min_depth_inv;   // 1/max_depth  (min_disp)
   float disp_range;      // 1/min_depth - 1/max_depth
   float si_thresh, si_var, smooth_w;
-  int use_si;
+  int si_scales;
+  float si_pred_mul, si_tgt_mul, si_lo, si_weight;
   // forward outputs
   float* partial;            // [nblk][NPART]
   unsigned char* sel;        // [4][B,H,W] argmin channel (0,1 identity; 2,3 warped)
@@ -337,11 +338,11 @@ __global__ void __launch_bounds__(NT) photoloss_fwd_kernel(PLArgs a) {
       a.sel[((long)s * a.B + b) * HW + o] = (unsigned char)idx;
       if (a.out_topt[s]) a.out_topt[s][(long)b * HW + o] = m;
       ps[0] += m;
-      if (a.use_si) {
+      if ((a.si_scales >> s) & 1) {
         float d = up_disp(disp, y, x, h, w, H, W);
-        float D = __fmul_rn(disp_to_depth(d, a.min_depth_inv, a.disp_range), 26.0f);
-        float Bm = __fmul_rn(a.beam[(long)b * HW + o], 100.0f);
-        bool valid = (Bm > 1.f) && (D < 80.f) && (D > 1.f) && (fabsf(__fadd_rn(D, -Bm)) < a.si_thresh);
+        float D = __fmul_rn(disp_to_depth(d, a.min_depth_inv, a.disp_range), a.si_pred_mul);
+        float Bm = __fmul_rn(a.beam[(long)b * HW + o], a.si_tgt_mul);
+        bool valid = (Bm > a.si_lo) && (D < 80.f) && (D > a.si_lo) && (fabsf(__fadd_rn(D, -Bm)) < a.si_thresh);
         if (valid) {
           float dl = __fadd_rn(logf(D), -logf(Bm));
           ps[1] += dl;
@@ -439,8 +440,8 @@ __global__ void smooth_fwd_kernel(SmArgs a) {
 //   stats[s*4+{0,1,2}] = n_s, mean(delta)_s, sqrt(var term)_s ; stats[16 + (b*4+s)] = L_sm of image b
 __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblk,
                                      const float* __restrict__ sm_partial, int B, int H, int W,
-                                     float si_var, float smooth_w, int use_si, float* losses,
-                                     float* stats) {
+                                     float si_var, float smooth_w, int si_scales, float si_weight,
+                                     float* losses, float* stats) {
   __shared__ double red[NPART * 32];
   __shared__ double tot[NPART];
   double acc[NPART];
@@ -475,13 +476,13 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblk
       double ls = photo + (double)smooth_w * sm / (double)(1 << s);
       losses[s] = (float)ls;
       total += ls;
-      if (use_si) {
+      if ((si_scales >> s) & 1) {
         double n = tot[s * 4 + 3];
         double m1 = tot[s * 4 + 1] / n, m2 = tot[s * 4 + 2] / n;
         double root = sqrt(m2 - (double)si_var * m1 * m1);
-        losses[4 + s] = (float)(0.1 * root);
+        losses[4 + s] = (float)((double)si_weight * root);
         stats[s * 4 + 0] = (float)n; stats[s * 4 + 1] = (float)m1; stats[s * 4 + 2] = (float)root;
-        total += 0.1 * root;
+        total += (double)si_weight * root;
       } else {
         losses[4 + s] = 0.f;
       }
@@ -695,17 +696,17 @@ __global__ void __launch_bounds__(NT) photoloss_bwd_kernel(PLBwdArgs ba) {
       if (y >= H || x >= W) continue;
       long o = (long)y * W + x;
       float g = gd[k];
-      if (a.use_si) {
+      if ((a.si_scales >> s) & 1) {
         float d = up_disp(disp, y, x, h, w, H, W);
         float depth = disp_to_depth(d, a.min_depth_inv, a.disp_range);
-        float D = __fmul_rn(depth, 26.0f);
-        float Bm = __fmul_rn(a.beam[(long)b * HW + o], 100.0f);
-        bool valid = (Bm > 1.f) && (D < 80.f) && (D > 1.f) && (fabsf(__fadd_rn(D, -Bm)) < a.si_thresh);
+        float D = __fmul_rn(depth, a.si_pred_mul);
+        float Bm = __fmul_rn(a.beam[(long)b * HW + o], a.si_tgt_mul);
+        bool valid = (Bm > a.si_lo) && (D < 80.f) && (D > a.si_lo) && (fabsf(__fadd_rn(D, -Bm)) < a.si_thresh);
         if (valid) {
           float n = ba.stats[s * 4 + 0], m1 = ba.stats[s * 4 + 1], root = ba.stats[s * 4 + 2];
           float dl = __fadd_rn(logf(D), -logf(Bm));
-          // d(0.1 sqrt(mean d^2 - v mean(d)^2))/d delta_i, then d delta/d depth = 1/depth
-          float coef = g_total * 0.25f * 0.1f * (dl - a.si_var * m1) / (n * root);
+          // d(w sqrt(mean d^2 - v mean(d)^2))/d delta_i, then d delta/d depth = 1/depth
+          float coef = g_total * 0.25f * a.si_weight * (dl - a.si_var * m1) / (n * root);
           g += coef * (-a.disp_range * depth);
         }
       }
@@ -833,7 +834,8 @@ int fill_args(PLArgs& a, const fd_photoloss_desc* d) {
   a.min_depth_inv = (float)(1.0 / (double)d->max_depth);
   a.disp_range = (float)(1.0 / (double)d->min_depth - 1.0 / (double)d->max_depth);
   a.si_thresh = d->si_thresh; a.si_var = d->si_var; a.smooth_w = d->smoothness;
-  a.use_si = d->use_si;
+  a.si_scales = d->beam ? d->si_scales : 0;
+  a.si_pred_mul = d->si_pred_mul; a.si_tgt_mul = d->si_tgt_mul; a.si_lo = d->si_lo; a.si_weight = d->si_weight;
   a.sel = d->sel;
   return 0;
 }
@@ -889,7 +891,7 @@ int fd_photoloss_fwd(const fd_photoloss_desc* d, float* losses, void* workspace,
   photoloss_fwd_kernel<<<grid, NT, 0, st>>>(a);
   FD_CHECK_LAUNCH();
   loss_finalize_kernel<<<1, 256, 0, st>>>(v.partial, (int)v.nblk, v.sm_partial, d->B, d->H, d->W,
-                                          d->si_var, d->smoothness, d->use_si, losses, v.stats);
+                                          d->si_var, d->smoothness, a.si_scales, d->si_weight, losses, v.stats);
   FD_CHECK_LAUNCH();
   return 0;
 }

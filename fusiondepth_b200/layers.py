@@ -4,20 +4,61 @@ Same public names, signatures and results, so ``from layers import *`` in the un
 trainer.py / refiner.py / completor.py / evaluate_depth.py resolves here (the drivers also pick
 up ``F``, ``nn``, ``np`` and ``torch`` from this namespace -- SURVEY.md section 0).
 
-``ConvBlock`` / ``Conv3x3`` run on the package's CUDA kernels.  The unfused geometry modules
-(``BackprojectDepth``, ``Project3D``, ``SSIM``, ``get_smooth_loss`` ...) are kept for API
-compatibility as thin tensor compositions; the product path does not call them -- the whole
-chain they form runs fused in ``fd_photoloss_fwd/bwd`` (see fusiondepth_b200.training).
+Everything with arithmetic in it runs on the package's CUDA kernels: ``ConvBlock`` / ``Conv3x3`` (conv
+kernels), ``transformation_from_parameters`` (fd_pose_matrix_*), ``BackprojectDepth`` / ``Project3D`` /
+``Cat_xy`` / ``SSIM`` (csrc/geometry.cu), and -- through the ``F`` proxy below -- the drivers' own
+``F.interpolate(bilinear)`` and ``F.grid_sample(border)`` calls.  So an UNPATCHED reference driver runs its
+whole loss chain on this library, op by op; ``training.patch_trainer`` swaps that chain for the fused
+``fd_photoloss_fwd/bwd`` pair, which is what the benchmark times.  There is no CPU fallback: the kernels
+reject CPU tensors.
 """
 from __future__ import absolute_import, division, print_function
+
+import types as _types
 
 import numpy as np
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
+import torch.nn.functional as _torch_F
 
 from . import ops as _ops
+
+
+class _FunctionalProxy(_types.ModuleType):
+    """``layers.F``: torch.nn.functional with the hot-path signatures routed to this library's kernels.
+
+    The drivers do ``from layers import *`` after their own ``import torch.nn.functional as F`` and
+    layers.py has no ``__all__``, so the ``F`` they end up using is *this* name.
+    Only the exact call shapes of the per-step path are intercepted -- bilinear ``interpolate`` with
+    ``align_corners=False`` to an explicit size (trainer.py:434, 579; refiner.py:325, 335, 680) and
+    ``grid_sample(padding_mode="border")`` (trainer.py:467) on 4-D fp32 CUDA tensors; every other
+    attribute is torch.nn.functional's own."""
+
+    def __getattr__(self, name):
+        return getattr(_torch_F, name)
+
+    @staticmethod
+    def _ours(t):
+        return isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4
+
+    def interpolate(self, input, size=None, scale_factor=None, mode="nearest", align_corners=None, **kw):
+        if (mode == "bilinear" and not align_corners and size is not None and scale_factor is None
+                and not kw and self._ours(input)):
+            size = tuple(int(v) for v in (size if isinstance(size, (list, tuple, torch.Size)) else (size, size)))
+            return _ops.upsample_bilinear(input, size[0], size[1])
+        return _torch_F.interpolate(input, size=size, scale_factor=scale_factor, mode=mode,
+                                    align_corners=align_corners, **kw)
+
+    def grid_sample(self, input, grid, mode="bilinear", padding_mode="zeros", align_corners=None):
+        if mode == "bilinear" and padding_mode == "border" and not align_corners and self._ours(input) \
+                and self._ours(grid):
+            return _ops.grid_sample_border(input, grid)
+        return _torch_F.grid_sample(input, grid, mode=mode, padding_mode=padding_mode,
+                                    align_corners=align_corners)
+
+
+F = _FunctionalProxy("fusiondepth_b200.layers.F")
 
 
 def disp_to_depth(disp, min_depth, max_depth):
@@ -59,6 +100,8 @@ def get_translation_matrix(translation_vector):
 def transformation_from_parameters(axisangle, translation, invert=False):
     """(axisangle, translation) -> 4x4; M = T@R, or R^T@T(-t) when inverting.
     Reference layers.py:23-40."""
+    if axisangle.is_cuda:
+        return _ops.pose_matrix(axisangle, translation, invert)       # one kernel each way
     R = rot_from_axisangle(axisangle)
     t = translation.clone()
     if invert:
@@ -77,14 +120,40 @@ class Conv3x3(nn.Module):
         self.conv = nn.Conv2d(int(in_channels), int(out_channels), 3)
         self.conv.weight.data = self.conv.weight.data.contiguous(memory_format=torch.channels_last)
 
-    def forward(self, x, act="none", segments=None):
-        """``segments`` (internal): un-assembled inputs [(a, b|None, upsample)], fused with the pad."""
+    def forward(self, x, act="none", segments=None, pad_out=False):
+        """``segments`` (internal): un-assembled inputs [(a, b|None, upsample)], fused with the pad.
+
+        Channel counts that are not multiples of 32 (the refine2d decoder's 262 / 134 / 102 / 22) are
+        zero-padded up to the next multiple so that the layer runs on the tensor-core kernels: the input by
+        an all-zero segment of the same gather, the weight by ops.pad_conv_params.  With ``pad_out`` the
+        OUTPUT keeps its zero-padded channels (they are exactly act(0) = 0 for ELU / ReLU) and the next
+        Conv3x3 consumes them as already-padded input."""
+        segs = list(segments) if segments is not None else [(x, None, False)]
+        w, b = self.conv.weight, self.conv.bias
+        cout, cin_w = w.shape[0], w.shape[1]
+        cin = sum(int(a.shape[1]) for a, _, _ in segs)
+        cin_p = cin
+        if cout != 1 and cin > 16 and cin % 32 != 0 and _ops.CONV_BACKEND == "tc":
+            cin_p = (cin + 31) // 32 * 32
+            a0, _, up0 = segs[0]
+            B = a0.shape[0]
+            H, W = a0.shape[2] * (2 if up0 else 1), a0.shape[3] * (2 if up0 else 1)
+            segs.append((_ops.zero_segment(B, cin_p - cin, H, W, a0.device), None, False))
+        cout_p = cout
+        if pad_out and cout > 16 and cout % 32 != 0 and _ops.CONV_BACKEND == "tc":
+            if act not in ("elu", "relu", "none"):
+                raise ValueError("pad_out needs an activation with act(0) == 0")
+            cout_p = (cout + 31) // 32 * 32
+        if cin_p != cin_w or cout_p != cout:
+            if cin_p < cin_w:
+                raise RuntimeError("Conv3x3: input has %d channels, weight expects %d" % (cin, cin_w))
+            w, b = _ops.pad_conv_params(w, b, cout_p, cin_p)
         if self.use_refl:
-            xp = _ops.assemble(segments if segments is not None else [(x, None, False)], pad=1)
-            return _ops.conv2d(xp, self.conv.weight, self.conv.bias, 1, 0, act)
-        if segments is not None:
-            x = _ops.assemble(segments, pad=0)
-        return _ops.conv2d(x, self.conv.weight, self.conv.bias, 1, 1, act)
+            xp = _ops.assemble(segs, pad=1)
+            return _ops.conv2d(xp, w, b, 1, 0, act)
+        if segments is not None or len(segs) > 1:
+            x = _ops.assemble(segs, pad=0)
+        return _ops.conv2d(x, w, b, 1, 1, act)
 
 
 class ConvBlock(nn.Module):
@@ -95,8 +164,8 @@ class ConvBlock(nn.Module):
         self.conv = Conv3x3(in_channels, out_channels)
         self.nonlin = nn.ELU(inplace=True)
 
-    def forward(self, x, segments=None):
-        return self.conv(x, act="elu", segments=segments)
+    def forward(self, x, segments=None, pad_out=False):
+        return self.conv(x, act="elu", segments=segments, pad_out=pad_out)
 
 
 def _pixel_grid(batch_size, height, width):
@@ -121,9 +190,9 @@ class BackprojectDepth(nn.Module):
         self.pix_coords = nn.Parameter(pix, requires_grad=False)
 
     def forward(self, depth, inv_K):
-        rays = torch.matmul(inv_K[:, :3, :3], self.pix_coords)
-        pts = depth.view(self.batch_size, 1, -1) * rays
-        return torch.cat([pts, self.ones], 1)
+        if depth.shape[0] != self.batch_size:
+            raise RuntimeError("BackprojectDepth was built for batch %d, got %d" % (self.batch_size, depth.shape[0]))
+        return _ops.backproject(depth, inv_K, self.height, self.width)
 
 
 class Cat_xy(nn.Module):
@@ -138,10 +207,9 @@ class Cat_xy(nn.Module):
         self.pix_coords = nn.Parameter(pix, requires_grad=False)
 
     def forward(self, depth, inv_K):
-        rays = torch.matmul(inv_K[:, :3, :3], self.pix_coords)
-        pts = (depth.view(self.batch_size, 1, -1) * rays).view(self.batch_size, 3, self.height, self.width)
-        x, y, z = pts[:, 0:1] / 30.0, pts[:, 1:2] / 2.0, (pts[:, 2:3] - 40) / 40.0
-        return torch.cat([x, y, z], 1)
+        if depth.shape[0] != self.batch_size:
+            raise RuntimeError("Cat_xy was built for batch %d, got %d" % (self.batch_size, depth.shape[0]))
+        return _ops.cat_xy(depth, inv_K, self.height, self.width)
 
 
 class Project3D(nn.Module):
@@ -152,17 +220,15 @@ class Project3D(nn.Module):
         self.batch_size, self.height, self.width, self.eps = batch_size, height, width, eps
 
     def forward(self, points, K, T):
-        P = torch.matmul(K, T)[:, :3, :]
-        cam = torch.matmul(P, points)
-        uv = cam[:, :2, :] / (cam[:, 2, :].unsqueeze(1) + self.eps)
-        uv = uv.view(self.batch_size, 2, self.height, self.width).permute(0, 2, 3, 1)
-        scale = uv.new_tensor([self.width - 1, self.height - 1])
-        return (uv / scale - 0.5) * 2
+        if points.shape[0] != self.batch_size:
+            raise RuntimeError("Project3D was built for batch %d, got %d" % (self.batch_size, points.shape[0]))
+        return _ops.project3d(points, K, T, self.height, self.width, self.eps)
 
 
 def upsample(x):
-    """Nearest x2.  Reference layers.py:229-232."""
-    return F.interpolate(x, scale_factor=2, mode="nearest")
+    """Nearest x2.  Reference layers.py:229-232.  (The decoder of this package never calls it: the upsample is
+    folded into the next convolution's gather, fd_assemble_fwd.)"""
+    return _torch_F.interpolate(x, scale_factor=2, mode="nearest")
 
 
 def get_smooth_loss(disp, img):
@@ -188,14 +254,7 @@ class SSIM(nn.Module):
         self.C1, self.C2 = 0.01 ** 2, 0.03 ** 2
 
     def forward(self, x, y):
-        x, y = self.refl(x), self.refl(y)
-        mx, my = self.mu_x_pool(x), self.mu_y_pool(y)
-        vx = self.sig_x_pool(x ** 2) - mx ** 2
-        vy = self.sig_y_pool(y ** 2) - my ** 2
-        vxy = self.sig_xy_pool(x * y) - mx * my
-        num = (2 * mx * my + self.C1) * (2 * vxy + self.C2)
-        den = (mx ** 2 + my ** 2 + self.C1) * (vx + vy + self.C2)
-        return torch.clamp((1 - num / den) / 2, 0, 1)
+        return _ops.ssim(x, y)
 
 
 def compute_depth_errors(gt, pred):

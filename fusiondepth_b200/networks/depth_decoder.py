@@ -22,7 +22,8 @@ class _DeepBlock(nn.Sequential):
     """Two ConvBlocks (`deep=True`, depth_decoder.py:27-33): keys ``{0,1}.conv.conv.*``."""
 
     def forward(self, x, segments=None):
-        return self[1](self[0](x, segments=segments))
+        # the first block keeps its zero-padded output channels (262 -> 288 ...), the second consumes them
+        return self[1](self[0](x, segments=segments, pad_out=True))
 
 
 class DepthDecoder(nn.Module):

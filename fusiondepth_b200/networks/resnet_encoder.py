@@ -172,7 +172,11 @@ class ResnetEncoder(nn.Module):
         # (x - 0.45) / 0.225 and the 7x7/2 stem in one op (normalised im2col rows -> GEMM)
         self.features.append(enc.bn1(ops.stem_conv(input_image, enc.conv1.weight), relu=True))
         x = ops.maxpool3x3s2(self.features[-1])
-        for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
+        for li, layer in enumerate((enc.layer1, enc.layer2, enc.layer3, enc.layer4)):
+            if li >= 2:
+                # bucketed gradient exchange: layer4's (then layer3's) gradients are complete once the
+                # backward pass reaches this point (training.bucket_of: layer4 -> 0, layer3 -> 1)
+                x = ops.grad_ready(x, 3 - li)
             for blk in layer:
                 x = blk(x)
             self.features.append(x)

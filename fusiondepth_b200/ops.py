@@ -35,17 +35,21 @@ def _direct_grad(p):
     return getattr(p, "_fd_grad", None) if (DIRECT_GRAD and p is not None) else None
 
 
-def _cached(key, make):
-    """make() -> tuple of tensors, computed once per step when the cache is on."""
+def _cached(key, make, persistent=True):
+    """make() -> tuple of tensors, computed once per step when the cache is on.  The key is a device
+    address, so only tensors that live for the whole step (parameters) may insert an entry: a temporary's
+    address can be handed to another layer by the allocator within the same step (`persistent=False`:
+    look up, never insert)."""
     if WEIGHT_CACHE is None:
         return make()
     hit = WEIGHT_CACHE.get(key)
     cur = torch.cuda.current_stream()
     if hit is None:
         val = make()
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        WEIGHT_CACHE[key] = (val, ev, cur)
+        if persistent:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            WEIGHT_CACHE[key] = (val, ev, cur)
         return val
     val, ev, owner = hit
     if owner != cur:
@@ -97,6 +101,11 @@ class BNSchedule:
 
 # Set by training.TrainStep while a step is being issued; None => nn.BatchNorm2d's in-place update.
 BN_SCHEDULE: Optional[BNSchedule] = None
+
+
+# Set by training.TrainStep when the gradient exchange is bucketed: callable(bucket_id), invoked from the
+# backward pass of every trunk once the gradients of that bucket have been launched (grad_ready()).
+GRAD_READY = None
 
 
 # Optional per-kernel-family timing (bench.py's roofline leg): when PROFILE is a dict, every
@@ -191,6 +200,8 @@ class Conv2dFn(torch.autograd.Function):
         lib = _lib.load()
         x = nhwc(x)
         w = nhwc(weight)
+        # derived tensors may be cached by address only for parameters stored channels-last in place
+        ctx.param_w = isinstance(weight, torch.nn.Parameter) and w.data_ptr() == weight.data_ptr()
         B, Cin, H, W = x.shape
         Cout, Cin_w, KH, KW = w.shape
         if Cin_w != Cin:
@@ -217,7 +228,7 @@ class Conv2dFn(torch.autograd.Function):
                 t = torch.empty(w.numel(), device=x.device, dtype=torch.float32)
                 _lib.check(lib.fd_tf32_split(_p(w), _p(t), w.numel(), _stream()), "fd_tf32_split")
                 return (t,)
-            (wlo,) = _cached((w.data_ptr(), "lo"), make_lo)
+            (wlo,) = _cached((w.data_ptr(), "lo"), make_lo, ctx.param_w)
             with _timed("conv", 2.0 * B * Ho * Wo * Cout * KH * KW * Cin):
                 _lib.check(lib.fd_conv2d_fwd_tc_stats(_p(x), _p(w), _p(wlo), _p(bias), _p(y), B, H, W, Cin,
                                                       Cout, KH, KW, stride, pad, act, _p(stats), _stream()),
@@ -278,7 +289,7 @@ class Conv2dFn(torch.autograd.Function):
                     _lib.check(lib.fd_weight_transpose_split(_p(w), _p(a), _p(b), Cout, KH * KW, Cin,
                                                              _stream()), "fd_weight_transpose_split")
                     return a, b
-                wt, wtlo = _cached((w.data_ptr(), "t"), make_t)
+                wt, wtlo = _cached((w.data_ptr(), "t"), make_t, ctx.param_w)
                 with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
                     _lib.check(lib.fd_conv2d_dgrad_tc(_p(dy), _p(wt), _p(wtlo), _p(dx), B, H, W, Cin,
                                                       Cout, KH, KW, stride, pad, st), "fd_conv2d_dgrad_tc")
@@ -303,6 +314,87 @@ class Conv2dFn(torch.autograd.Function):
         # gradients written straight into the parameters' buffers are not handed back to autograd
         return (dx, None if ctx.wg is not None else dw, None if ctx.bg is not None else dbias,
                 None, None, None, None)
+
+
+class PadConvParamsFn(torch.autograd.Function):
+    """Zero-pads a conv weight [Cout,Cin,KH,KW] (and bias) to [Cout_p,Cin_p,KH,KW] so that layers with channel
+    counts that are not multiples of 32 (the refine2d decoder's 262 / 134 / 102 / 22) run
+    on the tensor-core kernels; the gradient of the padded copy is folded back into the parameter's."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, cout_p, cin_p):
+        lib = _lib.load()
+        w = nhwc(weight)
+        Cout, Cin, KH, KW = w.shape
+        st = _stream()
+        wp = torch.empty((cout_p, cin_p, KH, KW), device=w.device, dtype=torch.float32, memory_format=CL)
+        if cout_p > Cout:
+            wp.zero_()
+        _lib.check(lib.fd_pad_rows(_p(w), _p(wp), Cout * KH * KW, Cin, cin_p, 0, st), "fd_pad_rows")
+        bp = None
+        if bias is not None:
+            bp = torch.zeros(cout_p, device=w.device, dtype=torch.float32)
+            bp[:Cout].copy_(bias)
+        ctx.cfg = (Cout, Cin, KH, KW, cout_p, cin_p, bias is not None)
+        ctx.wg, ctx.bg = _direct_grad(weight), _direct_grad(bias)
+        return wp, bp
+
+    @staticmethod
+    def backward(ctx, dwp, dbp):
+        lib = _lib.load()
+        Cout, Cin, KH, KW, cout_p, cin_p, has_bias = ctx.cfg
+        dwp = nhwc(dwp)
+        st = _stream()
+        if ctx.wg is not None:
+            _lib.check(lib.fd_pad_rows(_p(dwp), _p(ctx.wg), Cout * KH * KW, cin_p, Cin, 1, st), "fd_pad_rows")
+            dw = None
+        else:
+            dw = torch.zeros((Cout, Cin, KH, KW), device=dwp.device, dtype=torch.float32, memory_format=CL)
+            _lib.check(lib.fd_pad_rows(_p(dwp), _p(dw), Cout * KH * KW, cin_p, Cin, 1, st), "fd_pad_rows")
+        db = None
+        if has_bias and dbp is not None:
+            if ctx.bg is not None:
+                ctx.bg.add_(dbp[:Cout])
+            else:
+                db = dbp[:Cout].clone()
+        return dw, db, None, None
+
+
+def pad_conv_params(weight, bias, cout_p, cin_p):
+    return PadConvParamsFn.apply(weight, bias, int(cout_p), int(cin_p))
+
+
+_ZERO_SEGMENTS: Dict = {}
+
+
+def zero_segment(B, C, H, W, device):
+    """A constant all-zero [B,C,H,W] channels-last tensor (channel padding for assemble())."""
+    key = (B, C, H, W, str(device))
+    z = _ZERO_SEGMENTS.get(key)
+    if z is None:
+        z = _ZERO_SEGMENTS[key] = torch.zeros((B, C, H, W), device=device, dtype=torch.float32, memory_format=CL)
+    return z
+
+
+class GradReadyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bucket):
+        ctx.bucket = bucket
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if GRAD_READY is not None:
+            GRAD_READY(ctx.bucket)
+        return g, None
+
+
+def grad_ready(x, bucket: int):
+    """Marks the point of the forward pass after which all parameters belong to `bucket`'s predecessors in
+    backward order; a no-op unless a bucketed gradient exchange is active."""
+    if GRAD_READY is None or not (torch.is_grad_enabled() and x.requires_grad):
+        return x
+    return GradReadyFn.apply(x, int(bucket))
 
 
 def conv2d(x, weight, bias=None, stride=1, pad=0, act="none", stats=None):
@@ -628,7 +720,11 @@ class PhotoLossFn(torch.autograd.Function):
         desc.min_depth, desc.max_depth = opts.get("min_depth", 0.1), opts.get("max_depth", 100.0)
         desc.smoothness = opts.get("smoothness", 1e-3)
         desc.si_thresh, desc.si_var = opts.get("si_thresh", 2.0), opts.get("si_var", 0.3)
-        desc.use_si = int(opts.get("use_si", True))
+        # si-loss term: trainer.py:577-589 defaults; "use_si" False switches it off, "si_scales" is a bit
+        # mask of scales, the other keys select the refiner's GDC-clone variant (refiner.py:678-688)
+        desc.si_scales = int(opts.get("si_scales", 0xF)) if opts.get("use_si", True) else 0
+        desc.si_pred_mul, desc.si_tgt_mul = opts.get("si_pred_mul", 26.0), opts.get("si_tgt_mul", 100.0)
+        desc.si_lo, desc.si_weight = opts.get("si_lo", 1.0), opts.get("si_weight", 0.1)
         sel = torch.empty((4, B, H, W), device=dev, dtype=torch.uint8)
         desc.sel = sel.data_ptr()
         if outs is not None:
@@ -679,7 +775,264 @@ def photoloss(disps: Sequence[torch.Tensor], T_m1: torch.Tensor, T_p1: torch.Ten
 
 
 # --------------------------------------------------------------------------------------------
+# Unfused drop-in operators (csrc/geometry.cu): the layers.* modules and the layers.F proxy call these, so
+# that an UNPATCHED reference driver still runs its loss chain on this library's kernels.
+def _nchw(t):
+    return t.contiguous()
+
+
+class UpsampleBilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        _require_cuda(x, "upsample_bilinear")
+        x = _nchw(x)
+        B, C, h, w = x.shape
+        y = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_upsample_bilinear_fwd(_p(x), _p(y), B * C, h, w, H, W, _stream()),
+                   "fd_upsample_bilinear_fwd")
+        ctx.shape = (B, C, h, w, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, h, w, H, W = ctx.shape
+        dy = _nchw(dy)
+        dx = torch.empty((B, C, h, w), device=dy.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_upsample_bilinear_bwd(_p(dy), _p(dx), B * C, h, w, H, W, _stream()),
+                   "fd_upsample_bilinear_bwd")
+        return dx, None, None
+
+
+def upsample_bilinear(x, H, W):
+    """F.interpolate(x, [H, W], mode="bilinear", align_corners=False)."""
+    return UpsampleBilinearFn.apply(x, int(H), int(W))
+
+
+class BackprojectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K, H, W):
+        _require_cuda(depth, "backproject")
+        depth, inv_K = _nchw(depth), _nchw(inv_K)
+        B = depth.shape[0]
+        if depth.numel() != B * H * W or inv_K.shape != (B, 4, 4):
+            # the reference fails with a broadcasting RuntimeError when the batch differs from the ctor's
+            raise RuntimeError("BackprojectDepth: depth %s / inv_K %s do not match batch %d x %d x %d"
+                               % (tuple(depth.shape), tuple(inv_K.shape), B, H, W))
+        cam = torch.empty((B, 4, H * W), device=depth.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_backproject_fwd(_p(depth), _p(inv_K), _p(cam), B, H, W, _stream()),
+                   "fd_backproject_fwd")
+        ctx.save_for_backward(inv_K)
+        ctx.shape = (tuple(depth.shape), B, H, W)
+        return cam
+
+    @staticmethod
+    def backward(ctx, dcam):
+        (inv_K,) = ctx.saved_tensors
+        shape, B, H, W = ctx.shape
+        dcam = _nchw(dcam)
+        dd = torch.empty(shape, device=dcam.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_backproject_bwd(_p(dcam), _p(inv_K), _p(dd), B, H, W, _stream()),
+                   "fd_backproject_bwd")
+        return dd, None, None, None
+
+
+def backproject(depth, inv_K, H, W):
+    return BackprojectFn.apply(depth, inv_K, int(H), int(W))
+
+
+class Project3DFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, K, T, H, W, eps):
+        _require_cuda(points, "project3d")
+        points, K, T = _nchw(points), _nchw(K), _nchw(T)
+        B = points.shape[0]
+        if points.shape != (B, 4, H * W):
+            raise RuntimeError("Project3D: points %s do not match %d x 4 x %d" % (tuple(points.shape), B, H * W))
+        grid = torch.empty((B, H, W, 2), device=points.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_project3d_fwd(_p(points), _p(K), _p(T), _p(grid), B, H, W, eps, _stream()),
+                   "fd_project3d_fwd")
+        ctx.save_for_backward(points, K, T)
+        ctx.cfg = (B, H, W, eps)
+        return grid
+
+    @staticmethod
+    def backward(ctx, dgrid):
+        points, K, T = ctx.saved_tensors
+        B, H, W, eps = ctx.cfg
+        dgrid = _nchw(dgrid)
+        dp = torch.empty_like(points) if ctx.needs_input_grad[0] else None
+        dT = torch.empty_like(T) if ctx.needs_input_grad[2] else None
+        ws = torch.empty(B * 12, device=points.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_project3d_bwd(_p(points), _p(K), _p(T), _p(dgrid), _p(dp), _p(dT), B, H, W,
+                                                eps, _p(ws), _stream()), "fd_project3d_bwd")
+        return dp, None, dT, None, None, None
+
+
+def project3d(points, K, T, H, W, eps=1e-7):
+    if K.requires_grad:
+        raise NotImplementedError("project3d: no gradient wrt the intrinsics K")
+    return Project3DFn.apply(points, K, T, int(H), int(W), float(eps))
+
+
+class GridSampleBorderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, grid):
+        _require_cuda(img, "grid_sample")
+        img, grid = _nchw(img), _nchw(grid)
+        B, C, H, W = img.shape
+        if grid.dim() != 4 or grid.shape[0] != B or grid.shape[3] != 2:
+            raise RuntimeError("grid_sample: grid %s does not match input %s" % (tuple(grid.shape), tuple(img.shape)))
+        Ho, Wo = grid.shape[1], grid.shape[2]
+        out = torch.empty((B, C, Ho, Wo), device=img.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_grid_sample_border_fwd(_p(img), _p(grid), _p(out), B, C, H, W, Ho, Wo, _stream()),
+                   "fd_grid_sample_border_fwd")
+        ctx.save_for_backward(img, grid)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, grid = ctx.saved_tensors
+        B, C, H, W = img.shape
+        Ho, Wo = grid.shape[1], grid.shape[2]
+        dout = _nchw(dout)
+        dimg = torch.empty_like(img) if ctx.needs_input_grad[0] else None
+        dgrid = torch.empty_like(grid) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.load().fd_grid_sample_border_bwd(_p(img), _p(grid), _p(dout), _p(dgrid), _p(dimg), B, C,
+                                                         H, W, Ho, Wo, _stream()), "fd_grid_sample_border_bwd")
+        return dimg, dgrid
+
+
+def grid_sample_border(img, grid):
+    """F.grid_sample(img, grid, mode="bilinear", padding_mode="border", align_corners=False)."""
+    return GridSampleBorderFn.apply(img, grid)
+
+
+class SSIMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        _require_cuda(x, "ssim")
+        x, y = _nchw(x), _nchw(y)
+        if x.shape != y.shape or x.dim() != 4:
+            raise RuntimeError("ssim: shapes %s / %s" % (tuple(x.shape), tuple(y.shape)))
+        B, C, H, W = x.shape
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().fd_ssim_fwd(_p(x), _p(y), _p(out), B * C, H, W, _stream()), "fd_ssim_fwd")
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dout = _nchw(dout)
+        lib = _lib.load()
+        ws = torch.empty(3 * x.numel(), device=x.device, dtype=torch.float32)
+        dx = dy = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.check(lib.fd_ssim_bwd(_p(x), _p(y), _p(dout), _p(dx), B * C, H, W, _p(ws), _stream()), "fd_ssim_bwd")
+        if ctx.needs_input_grad[1]:
+            dy = torch.empty_like(y)
+            _lib.check(lib.fd_ssim_bwd(_p(y), _p(x), _p(dout), _p(dy), B * C, H, W, _p(ws), _stream()), "fd_ssim_bwd")
+        return dx, dy
+
+
+def ssim(x, y):
+    return SSIMFn.apply(x, y)
+
+
+class PoseMatrixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        _require_cuda(axisangle, "pose_matrix")
+        aa = axisangle.contiguous().view(-1, 3)
+        tr = translation.contiguous().view(-1, 3)
+        B = aa.shape[0]
+        if tr.shape[0] != B:
+            raise RuntimeError("transformation_from_parameters: %s vs %s" % (tuple(axisangle.shape),
+                                                                             tuple(translation.shape)))
+        M = torch.empty((B, 4, 4), device=aa.device, dtype=torch.float32)
+        _lib.check(_lib.load().fd_pose_matrix_fwd(_p(aa), _p(tr), int(invert), _p(M), B, _stream()),
+                   "fd_pose_matrix_fwd")
+        ctx.save_for_backward(aa, tr)
+        ctx.cfg = (int(invert), axisangle.shape, translation.shape)
+        return M
+
+    @staticmethod
+    def backward(ctx, dM):
+        aa, tr = ctx.saved_tensors
+        invert, sa, st = ctx.cfg
+        dM = dM.contiguous()
+        daa, dtr = torch.empty_like(aa), torch.empty_like(tr)
+        _lib.check(_lib.load().fd_pose_matrix_bwd(_p(aa), _p(tr), invert, _p(dM), _p(daa), _p(dtr), aa.shape[0],
+                                                  _stream()), "fd_pose_matrix_bwd")
+        return daa.view(sa), dtr.view(st), None
+
+
+def pose_matrix(axisangle, translation, invert=False):
+    """layers.transformation_from_parameters: [B,1,3] x 2 -> [B,4,4], one kernel each way."""
+    return PoseMatrixFn.apply(axisangle, translation, bool(invert))
+
+
+def cat_xy(depth, inv_K, H, W):
+    """layers.Cat_xy.forward.  No gradient (the refiner calls it under no_grad, refiner.py:306-346)."""
+    _require_cuda(depth, "cat_xy")
+    if depth.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("Cat_xy: no gradient wrt depth (the reference uses it under no_grad)")
+    depth, inv_K = _nchw(depth), _nchw(inv_K)
+    B = depth.shape[0]
+    if depth.numel() != B * H * W or inv_K.shape != (B, 4, 4):
+        raise RuntimeError("Cat_xy: depth %s / inv_K %s do not match batch %d x %d x %d"
+                           % (tuple(depth.shape), tuple(inv_K.shape), B, H, W))
+    out = torch.empty((B, 3, H, W), device=depth.device, dtype=torch.float32)
+    _lib.check(_lib.load().fd_cat_xy(_p(depth), _p(inv_K), _p(out), B, H, W, _stream()), "fd_cat_xy")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def refine_pack(disp0, beam, two_cha, inv_Ks, crop=(78, 190, 23, 617), min_depth=0.1, max_depth=100.0):
+    """The stage-2 pseudo-3D maps of refiner.py:316-346 (fd_refine_pack).  Returns ([B,6,h,w] x 4 stored
+    channels-last, ratios[4]).  No gradient: the reference builds these under no_grad."""
+    _require_cuda(disp0, "refine_pack")
+    lib = _lib.load()
+    with torch.no_grad():
+        disp0, beam, two_cha = _nchw(disp0.detach()), _nchw(beam), _nchw(two_cha)
+        B, _, H, W = disp0.shape
+        if beam.numel() != B * H * W or two_cha.shape != (B, 2, H, W):
+            raise RuntimeError("refine_pack: beam %s / two_cha %s do not match disp %s"
+                               % (tuple(beam.shape), tuple(two_cha.shape), tuple(disp0.shape)))
+        iks = [_nchw(k) for k in inv_Ks]
+        outs = [empty_nhwc(B, 6, H >> s, W >> s, disp0.device) for s in range(4)]
+        ratios = torch.empty(4, device=disp0.device, dtype=torch.float32)
+        ws = torch.empty(lib.fd_refine_pack_workspace_bytes(B, H, W) // 4, device=disp0.device, dtype=torch.float32)
+        ik_arr = (c_void_p * 4)(*[t.data_ptr() for t in iks])
+        out_arr = (c_void_p * 4)(*[t.data_ptr() for t in outs])
+        _lib.check(lib.fd_refine_pack(_p(disp0), _p(beam), _p(two_cha), ctypes.byref(ik_arr), B, H, W,
+                                      int(crop[0]), int(crop[1]), int(crop[2]), int(crop[3]), min_depth, max_depth,
+                                      ctypes.byref(out_arr), _p(ratios), _p(ws), _stream()), "fd_refine_pack")
+    return outs, ratios
+
+
+def masked_median(x, mask_src, window=None, scale=1.0):
+    """torch.median((x * scale)[mask_src > 0 inside window]) -- lower median, 0-dim tensor (refiner.py:332)."""
+    _require_cuda(x, "masked_median")
+    lib = _lib.load()
+    x, mask_src = _nchw(x.detach()), _nchw(mask_src)
+    if x.shape != mask_src.shape:
+        raise RuntimeError("masked_median: shapes %s / %s" % (tuple(x.shape), tuple(mask_src.shape)))
+    H, W = x.shape[-2:]
+    B = x.numel() // (H * W)
+    y0, y1, x0, x1 = window if window is not None else (0, H, 0, W)
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    ws = torch.empty(lib.fd_masked_median_workspace_bytes(B, H, W) // 4, device=x.device, dtype=torch.float32)
+    _lib.check(lib.fd_masked_median(_p(x), _p(mask_src), B, H, W, int(y0), int(y1), int(x0), int(x1), float(scale),
+                                    _p(out), _p(ws), _stream()), "fd_masked_median")
+    return out[0]
+
+
+# --------------------------------------------------------------------------------------------
 def adam_step(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
-    """In-place Adam on flat fp32 buffers; `state` is a 4-word int32 device tensor (step counter)."""
+    """In-place Adam on flat fp32 buffers; `state` is a 4-word int32 device tensor (step counter, ...,
+    learning rate as float bits in word 3 -- used when lr < 0)."""
     _lib.check(_lib.load().fd_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
                                         _p(state), grad_scale, _stream()), "fd_adam_step")

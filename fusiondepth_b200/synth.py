@@ -185,6 +185,20 @@ def make_batch(B: int, H: int, W: int, seed: int = 1,
     return inputs
 
 
+def make_refiner_batch(B: int, H: int, W: int, seed: int = 1, **kw) -> Dict:
+    """A stage-2 (refiner.py) micro-batch: the stage-1 batch + ``inf_gdc`` [B,H,W], the GDC-corrected
+    depth the refiner clones (refiner.py:678-688).  With random-init weights the refined depth is
+    ~0.2..2 m (no x26 in the refiner), so inf_gdc ~ U[0.05, 2.0] keeps the GDC mask populated
+    (SURVEY.md section 8(c)/(d)); ~30 % of it is zero like real GDC output (pixels without a value)."""
+    kw.setdefault("mode", "coherent")
+    kw.setdefault("lidar_density", 0.05)
+    inputs = make_batch(B, H, W, seed=seed, **kw)
+    g = torch.Generator().manual_seed(seed + 17)
+    gdc = 0.05 + 1.95 * torch.rand(B, H, W, generator=g)
+    inputs["inf_gdc"] = gdc * (torch.rand(B, H, W, generator=g) > 0.3).float()
+    return inputs
+
+
 def to_device(inputs: Dict, device) -> Dict:
     out = {}
     for k, v in inputs.items():

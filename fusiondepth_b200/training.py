@@ -60,19 +60,21 @@ def predict_poses(models, inputs, frame_ids=(0, -1, 1)):
     return outputs
 
 
-def loss_static(inputs, noise, frame_ids=(0, -1, 1)):
-    """Non-differentiable operands of the fused loss, gathered from the loader's dict."""
+def loss_static(inputs, noise, frame_ids=(0, -1, 1), si_target="4beam"):
+    """Non-differentiable operands of the fused loss, gathered from the loader's dict.  `si_target`: the
+    map the scale-invariant term compares against ("4beam" in trainer.py:577-589, "inf_gdc" in
+    refiner.py:678-688)."""
     color = {}
     for s in range(4):
         color[(0, s)] = inputs[("color", 0, s)]
     for f in frame_ids[1:]:
         color[(f, 0)] = inputs[("color", f, 0)]
     return {"color": color, "K": inputs[("K", 0)], "inv_K": inputs[("inv_K", 0)],
-            "beam": inputs["4beam"], "noise": noise}
+            "beam": inputs[si_target], "noise": noise}
 
 
 def fused_losses(inputs, outputs, noise, opts: Optional[Dict] = None, materialize: bool = False,
-                 frame_ids=(0, -1, 1)):
+                 frame_ids=(0, -1, 1), si_target="4beam"):
     """generate_images_pred + compute_losses (trainer.py:425-596) in two kernel launches.
     Returns the reference's ``losses`` dict; with ``materialize`` the per-scale
     ("depth",0,s), ("color",f,s), identity_selection/s tensors are written into ``outputs``."""
@@ -80,7 +82,7 @@ def fused_losses(inputs, outputs, noise, opts: Optional[Dict] = None, materializ
     disps = [outputs[("disp", s)] for s in range(4)]
     lv = ops.photoloss(disps, outputs[("cam_T_cam", 0, frame_ids[1])],
                        outputs[("cam_T_cam", 0, frame_ids[2])],
-                       loss_static(inputs, noise, frame_ids), opts, outs)
+                       loss_static(inputs, noise, frame_ids, si_target), opts, outs)
     losses = {name: lv[i] for i, name in enumerate(ops.LOSS_NAMES)}
     if materialize:
         sel = outs.pop("sel")
@@ -172,11 +174,20 @@ def patch_trainer(trainer, materialize: bool = True):
         raise NotImplementedError("patch_trainer covers the reference's default loss configuration")
     opts = {"min_depth": opt.min_depth, "max_depth": opt.max_depth,
             "smoothness": opt.disparity_smoothness, "si_thresh": opt.gdc_loss_threshold,
-            "si_var": opt.si_var,
-            "use_si": opt.trainer_siloss == "true" and opt.trainer_siloss_all_scale}
+            "si_var": opt.si_var, "use_si": opt.trainer_siloss == "true",
+            # trainer.py:578: every scale with --trainer_siloss_all_scale (default on), else scale 0 only
+            "si_scales": 0xF if opt.trainer_siloss_all_scale else 0x1}
 
     def generate_images_pred(inputs, outputs, frame_ids):
-        return None                                   # done inside the fused loss launch
+        if len(frame_ids) > 1:
+            return None                               # done inside the fused loss launch
+        # validation (Trainer.val -> process_batch(val=True), trainer.py:305-307): no source frames and no
+        # compute_losses afterwards, but compute_depth_losses reads ("depth", 0, s) (trainer.py:604)
+        H, W = opt.height, opt.width
+        for s in opt.scales:
+            up = ops.upsample_bilinear(outputs[("disp", s)], H, W)
+            outputs[("depth", 0, s)] = 1.0 / (1.0 / opt.max_depth + (1.0 / opt.min_depth - 1.0 / opt.max_depth) * up)
+        return None
 
     def compute_losses(inputs, outputs):
         B, _, H, W = inputs[("color", 0, 0)].shape
@@ -196,31 +207,43 @@ class FlatParams:
 
     ALIGN = 64      # floats: every parameter starts on a 256 B boundary (float4 / TMA loads)
 
-    def __init__(self, models: Dict[str, nn.Module]):
-        params: List[nn.Parameter] = []
+    def __init__(self, models: Dict[str, nn.Module], order=None):
+        """`order(name, param_name) -> sortable`: optional bucket key; parameters are laid out in ascending
+        key order (the gradient exchange sends contiguous bucket slices).  Parameters with requires_grad
+        False (the refiner's frozen stage-1 networks) come last: they share the weight buffer (and its
+        derived W_lo / W^T copies) but have no gradient slot and are not touched by Adam."""
+        named = []
         for name in models:
-            params += [p for p in models[name].parameters() if p.requires_grad]
-        self.params = params
+            for k, p in models[name].named_parameters():
+                named.append(((0 if p.requires_grad else 1, order(name, k) if order else 0, len(named)), name, k, p))
+        named.sort(key=lambda t: t[0])
+        self.names = [(name, k) for _, name, k, _ in named]
+        self.params = [p for _, _, _, p in named]
+        self.keys = [key[1] for key, _, _, _ in named]
         A = self.ALIGN
-        n = sum((p.numel() + A - 1) // A * A for p in params)
-        dev = params[0].device
+        pad = lambda k: (k + A - 1) // A * A
+        n = sum(pad(p.numel()) for p in self.params)
+        self.n_train = sum(pad(p.numel()) for p in self.params if p.requires_grad)
+        dev = self.params[0].device
         self.data = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
-        off = 0
-        for p in params:
-            k = p.numel()
-            dv, gv = self._view(self.data[off:off + k], p), self._view(self.grad[off:off + k], p)
-            dv.copy_(p.data)
-            p.data = dv
-            p.grad = gv
-            p._fd_grad = gv          # ops.DIRECT_GRAD: backward kernels add into this view
-            off += (k + A - 1) // A * A
-        self.numel = n
+        self.grad = torch.zeros(self.n_train, device=dev, dtype=torch.float32)
         self.offsets = {}
         off = 0
-        for p in params:
+        for p in self.params:
+            k = p.numel()
+            if p.dim() == 4 and not p.is_contiguous(memory_format=torch.channels_last):
+                # the kernels read/write conv weights as [Cout,KH,KW,Cin]
+                p.data = p.data.contiguous(memory_format=torch.channels_last)
+            dv = self._view(self.data[off:off + k], p)
+            dv.copy_(p.data)
+            p.data = dv
+            if p.requires_grad:
+                gv = self._view(self.grad[off:off + k], p)
+                p.grad = gv
+                p._fd_grad = gv          # ops.DIRECT_GRAD: backward kernels add into this view
             self.offsets[p] = off
-            off += (p.numel() + A - 1) // A * A
+            off += pad(k)
+        self.numel = n
         # derived conv-weight tensors (W_lo, W^T, W^T_lo) live in flat buffers with the same layout and
         # are refreshed by two launches per optimiser step (prepare_weights)
         self.lo = None
@@ -272,23 +295,59 @@ class FlatParams:
 
     @staticmethod
     def _view(flat, p):
-        if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+        if p.dim() == 4:
             o, i, kh, kw = p.shape
             return flat.view(o, kh, kw, i).permute(0, 3, 1, 2)
         return flat.view(p.shape)
+
+    def bucket_slices(self):
+        """[(key, start, end)] over the trainable part of the buffer, one entry per distinct order key."""
+        out, start, cur = [], 0, None
+        A = self.ALIGN
+        off = 0
+        for p, key in zip(self.params, self.keys):
+            if not p.requires_grad:
+                break
+            if cur is None:
+                cur = key
+            if key != cur:
+                out.append((cur, start, off))
+                start, cur = off, key
+            off += (p.numel() + A - 1) // A * A
+        if cur is not None:
+            out.append((cur, start, off))
+        return out
 
     def zero_grad(self):
         self.grad.zero_()
 
 
-def reduce_gradients(flat: "FlatParams", world: int, group=None):
-    """The data-parallel exchange step: ONE sum all-reduce of the flat gradient buffer (NCCL over
-    NVLink on GPUs; the 1/world average is folded into the Adam kernel's grad_scale).  Samples are
-    independent through the whole step and BatchNorm statistics stay per rank, as in the
+def reduce_gradients(flat: "FlatParams", world: int, group=None, lo: int = 0, hi: Optional[int] = None):
+    """The data-parallel exchange step: a sum all-reduce of (a bucket slice of) the flat gradient buffer
+    (NCCL over NVLink on GPUs; the 1/world average is folded into the Adam kernel's grad_scale).  Samples
+    are independent through the whole step and BatchNorm statistics stay per rank, as in the
     single-process reference, so this is the only collective on the path."""
     if world > 1:
-        torch.distributed.all_reduce(flat.grad, op=torch.distributed.ReduceOp.SUM, group=group)
+        buf = flat.grad if (lo == 0 and hi is None) else flat.grad[lo:hi]
+        torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=group)
     return flat.grad
+
+
+# Gradient buckets in the order their gradients complete during the backward pass (SURVEY.md section 8(e)):
+# 0 = both decoders' heads + every trunk's layer4 (72 % of a ResNet-18's parameters, finished first),
+# 1 = layer3, 2 = the rest of the trunks.  The never-used ImageNet `fc` heads (resnet_encoder.py:74,
+# grad=None in the reference) are placed last and excluded from the exchange.
+N_BUCKETS = 3
+
+
+def bucket_of(model_name: str, param_name: str) -> int:
+    if ".fc." in param_name:
+        return N_BUCKETS
+    if model_name in ("depth", "pose", "refine2d_decoder") or ".layer4." in param_name:
+        return 0
+    if ".layer3." in param_name:
+        return 1
+    return 2
 
 
 class TrainStep:
@@ -298,20 +357,36 @@ class TrainStep:
 
     def __init__(self, models, lr: float = 1e-4, accumulate: int = 1, opts: Optional[Dict] = None,
                  process_group=None, parallel_trunks: bool = True, direct_grad: bool = True,
-                 cache_weight_prep: bool = True, concurrent_microbatches: bool = True):
+                 cache_weight_prep: bool = True, concurrent_microbatches: bool = True,
+                 bucketed_allreduce: bool = True):
         self.models = models
         self.accumulate = accumulate
-        self.lr = float(lr)
         self.opts = opts
-        self.flat = FlatParams(models)
+        self.flat = FlatParams(models, order=bucket_of)
         dev = self.flat.data.device
-        self.exp_avg = torch.zeros_like(self.flat.data)
-        self.exp_avg_sq = torch.zeros_like(self.flat.data)
+        nt = self.flat.n_train
+        self.exp_avg = torch.zeros(nt, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(nt, device=dev, dtype=torch.float32)
+        # word 0: step counter, words 1-2: bias-correction scalars, word 3: learning rate (float bits) --
+        # all on the device so that a captured graph follows set_lr() / the step count
         self.adam_state = torch.zeros(4, device=dev, dtype=torch.int32)
+        self.set_lr(lr)
+        self.lr0 = float(lr)
         self.pg = process_group
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        if self.world > 1:
+            # replicas must start from the same weights and BatchNorm buffers (rank 0's)
+            torch.distributed.broadcast(self.flat.data, 0, group=process_group)
+            for m in models.values():
+                for b in m.buffers():
+                    torch.distributed.broadcast(b, 0, group=process_group)
+        self.buckets = [(k, lo, hi) for k, lo, hi in self.flat.bucket_slices() if k < N_BUCKETS]
+        self.bucketed = bool(bucketed_allreduce) and self.world > 1 and len(self.buckets) > 1 \
+            and os.environ.get("FD_BUCKETED_ALLREDUCE", "1") != "0"
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.bucketed else None
+        self._ready = None
         self.direct_grad, self.cache_weight_prep = direct_grad, cache_weight_prep
         # The micro-batches of a step are independent given the weights (gradients accumulate with
         # atomics, BatchNorm running statistics through ops.BNSchedule), so each gets its own stream
@@ -332,6 +407,23 @@ class TrainStep:
         for m in models.values():
             m.train()
 
+    def set_lr(self, lr: float):
+        """Learning rate of the following steps (StepLR: trainer.py:131-132, 266).  Lives on the device, so
+        it also reaches a captured graph's replays."""
+        self.lr = float(lr)
+        self.adam_state[3:4].copy_(torch.tensor([self.lr], dtype=torch.float32).view(torch.int32))
+
+    def step_lr_schedule(self, epoch: int, step_size: int, gamma: float = 0.1, base_lr: Optional[float] = None):
+        """optim.lr_scheduler.StepLR(step_size, gamma) evaluated at `epoch` (trainer.py:131-132)."""
+        base = self.lr0 if base_lr is None else base_lr
+        self.set_lr(base * gamma ** (epoch // step_size))
+
+    def _grad_ready(self, bucket: int):
+        """Backward hook (ops.GRAD_READY): the gradients of `bucket` of this trunk call are on the stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._ready[bucket].append(ev)
+
     def _make_bn_schedule(self):
         """Calls per optimiser step of every BatchNorm layer: the pose trunks see both image pairs
         of a micro-batch (trainer.py:339-365), every other trunk one batch."""
@@ -350,6 +442,9 @@ class TrainStep:
         ops.DIRECT_GRAD = self.direct_grad
         ops.WEIGHT_CACHE = {} if self.cache_weight_prep else None
         ops.BN_SCHEDULE = self.bn_schedule
+        if self.bucketed:
+            self._ready = [[] for _ in range(N_BUCKETS)]
+            ops.GRAD_READY = self._grad_ready
         try:
             if self.bn_schedule is not None:
                 self.bn_schedule.begin_step()
@@ -363,6 +458,7 @@ class TrainStep:
             ops.DIRECT_GRAD = False
             ops.WEIGHT_CACHE = None
             ops.BN_SCHEDULE = None
+            ops.GRAD_READY = None
 
     def _micro_batch(self, inputs, noise, trunks):
         _, losses = process_batch(self.models, inputs, noise, self.opts, streams=trunks)
@@ -392,10 +488,34 @@ class TrainStep:
             for inputs, noise in zip(batches, noises):
                 part = self._micro_batch(inputs, noise, self.trunks[0])
                 total = part if total is None else total + part
-        reduce_gradients(self.flat, self.world, self.pg)
-        ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.adam_state,
-                      self.lr, grad_scale=1.0 / self.world)
+        self._exchange_and_update()
         return total
+
+    def _exchange_and_update(self):
+        """Gradient exchange + Adam.  Bucketed: the all-reduce of a bucket is issued on a communication
+        stream that waits only for that bucket's backward kernels (events recorded by ops.GRAD_READY hooks
+        inside every trunk), so inside the captured graph it runs under the rest of the backward pass;
+        only the last bucket (layers 1-2 and the stems) is exposed."""
+        nt = self.flat.n_train
+        if self.world > 1:
+            end = self.buckets[-1][2] if self.buckets else nt       # the unused fc heads are not exchanged
+            if self.bucketed:
+                cur = torch.cuda.current_stream()
+                cs = self.comm_stream
+                for k, lo, hi in self.buckets[:-1]:
+                    for ev in self._ready[k]:
+                        cs.wait_event(ev)
+                    with torch.cuda.stream(cs):
+                        reduce_gradients(self.flat, self.world, self.pg, lo, hi)
+                cs.wait_stream(cur)
+                with torch.cuda.stream(cs):
+                    k, lo, hi = self.buckets[-1]
+                    reduce_gradients(self.flat, self.world, self.pg, lo, hi)
+                cur.wait_stream(cs)
+            else:
+                reduce_gradients(self.flat, self.world, self.pg, 0, end)
+        ops.adam_step(self.flat.data[:nt], self.flat.grad, self.exp_avg, self.exp_avg_sq, self.adam_state,
+                      -1.0, grad_scale=1.0 / self.world)
 
     def step(self, batches: Sequence[Dict], noises: Sequence[Dict]):
         assert len(batches) == self.accumulate

@@ -71,11 +71,18 @@ typedef struct fd_photoloss_desc {
   const float* inv_K;         /* [B,4,4] ("inv_K",0) */
   const float* T[2];          /* [B,4,4] cam_T_cam for frames -1, +1 */
   const float* noise[4];      /* [B,2,H,W] the randn of trainer.py:551 per scale */
-  const float* beam;          /* [B,1,H,W] inputs["4beam"] */
+  const float* beam;          /* [B,1,H,W] si-loss target: inputs["4beam"] (trainer.py:577-589) or
+                                 inputs["inf_gdc"] (refiner.py:678-688) */
   float min_depth, max_depth; /* options.py:64-71 (0.1, 100) */
   float smoothness;           /* disparity_smoothness 1e-3 */
   float si_thresh, si_var;    /* gdc_loss_threshold 2.0, si_var 0.3 */
-  int use_si;                 /* trainer_siloss on all scales */
+  /* Scale-invariant log term: D = si_pred_mul * depth, G = si_tgt_mul * target,
+   * valid = G > si_lo && D < 80 && D > si_lo && |D - G| < si_thresh,
+   * loss = si_weight * sqrt(mean d^2 - si_var * mean(d)^2), d = ln D - ln G over valid pixels.
+   * trainer.py:577-589: (26, 100, 1, 0.1) on every scale (bit s of si_scales; only scale 0 without
+   * --trainer_siloss_all_scale); refiner.py:557-563, 678-688: (1, 1, 1e-3, 10 * 0.008 * 4) on scale 0. */
+  int si_scales;
+  float si_pred_mul, si_tgt_mul, si_lo, si_weight;
   unsigned char* sel;         /* [4,B,H,W] out: argmin channel (0,1 identity; 2,3 warped) */
   float* out_depth[4];        /* optional [B,1,H,W] ("depth",0,s) */
   float* out_color[4][2];     /* optional [B,3,H,W] ("color",f,s) */
@@ -90,6 +97,63 @@ int fd_photoloss_fwd(const fd_photoloss_desc* desc_host, float* losses, void* wo
 int fd_photoloss_bwd(const fd_photoloss_desc* desc_host, const float* grad_loss,
                      float* const grad_disp[4], float* grad_T0, float* grad_T1, void* workspace,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Unfused drop-in operators: what layers.BackprojectDepth / Project3D / SSIM and the F.interpolate /
+ * F.grid_sample calls of the UNCHANGED drivers resolve to (trainer.py:434-470, 479-486, 579;
+ * refiner.py:325-335; evaluate_depth.py:207-218) when the fused fd_photoloss_* pair is not patched in.
+ * fp32 NCHW contiguous tensors; `planes` = B*C.
+ *   upsample_bilinear: F.interpolate(mode="bilinear", align_corners=False), any in/out size;
+ *   backproject:  cam [B,4,HW] = [depth * (inv_K[:3,:3] @ [x,y,1]); 1]           (layers.py:133-162)
+ *   project3d:    grid [B,H,W,2] = ((K@T)[:3] @ pts -> /(z+eps) -> /(W-1),(H-1) - .5) * 2  (layers.py:204-226);
+ *                 bwd: dpoints [B,4,HW] (optional) and dT [B,4,4] (optional), workspace B*12 floats;
+ *   grid_sample_border: bilinear, padding_mode="border", align_corners=False; bwd: dgrid and/or dimg;
+ *   ssim: clamp((1 - SSIM)/2, 0, 1) over 3x3 reflect-padded windows (layers.py:251-281); bwd is the
+ *         gradient wrt the first argument (swap the arguments for the second), workspace 3*planes*H*W floats.
+ * ---------------------------------------------------------------------------------------- */
+int fd_upsample_bilinear_fwd(const float* x, float* y, long planes, int h, int w, int H, int W, void* stream);
+int fd_upsample_bilinear_bwd(const float* dy, float* dx, long planes, int h, int w, int H, int W, void* stream);
+int fd_backproject_fwd(const float* depth, const float* inv_K, float* cam, int B, int H, int W, void* stream);
+int fd_backproject_bwd(const float* dcam, const float* inv_K, float* ddepth, int B, int H, int W, void* stream);
+int fd_project3d_fwd(const float* points, const float* K, const float* T, float* grid, int B, int H, int W,
+                     float eps, void* stream);
+int fd_project3d_bwd(const float* points, const float* K, const float* T, const float* dgrid, float* dpoints,
+                     float* dT, int B, int H, int W, float eps, void* workspace, void* stream);
+int fd_grid_sample_border_fwd(const float* img, const float* grid, float* out, int B, int C, int H, int W,
+                              int Ho, int Wo, void* stream);
+int fd_grid_sample_border_bwd(const float* img, const float* grid, const float* dout, float* dgrid, float* dimg,
+                              int B, int C, int H, int W, int Ho, int Wo, void* stream);
+/* transformation_from_parameters (layers.py:23-97): axisangle, translation [B,3] -> M [B,4,4]
+ * (M = T @ R, or R^T @ T(-t) when invert); bwd: dM -> d_axisangle, d_translation [B,3]. */
+int fd_pose_matrix_fwd(const float* axisangle, const float* translation, int invert, float* M, int B, void* stream);
+int fd_pose_matrix_bwd(const float* axisangle, const float* translation, int invert, const float* dM,
+                       float* d_axisangle, float* d_translation, int B, void* stream);
+/* Cat_xy (layers.py:165-201): depth [B,1,H,W], inv_K [B,4,4] -> [B,3,H,W] = (X/30, Y/2, (Z-40)/40) */
+int fd_cat_xy(const float* depth, const float* inv_K, float* out, int B, int H, int W, void* stream);
+int fd_ssim_fwd(const float* x, const float* y, float* out, long planes, int H, int W, void* stream);
+int fd_ssim_bwd(const float* x, const float* y, const float* dout, float* dx, long planes, int H, int W,
+                void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage-2 (refiner.py) pseudo-3D pack -- replaces refiner.py:316-346 (default flags refine_a0='true',
+ * catxy='true') and layers.Cat_xy (layers.py:165-201): per scale s, the stage-1 disparity max-pooled s
+ * times -> bilinear to HxW -> depth -> rescaled by ONE ratio per batch,
+ * median(beam[mask]*100) / median(depth[mask]) (torch.median = lower median; mask = beam > 0 inside
+ * rows [crop_y0,crop_y1) x cols [crop_x0,crop_x1), reference 78:190 x 23:617) -> 6-channel map
+ * [scaled_disp | x/30, y/2, (z-40)/40 | max-pooled 2-channel LiDAR].  No gradient (the reference
+ * builds these under no_grad).
+ *   disp0 [B,1,H,W]; beam [B,1,H,W]; two_cha [B,2,H,W] NCHW; inv_K[s] [B,4,4] of scale s;
+ *   out[s] [B,H>>s,W>>s,6] NHWC; ratios [4] (out, one per scale).
+ * fd_masked_median: out[0] = lower median of x[i]*scale over {i in window : mask_src[i] > 0} (NaN when
+ * the set is empty) -- the torch.median(x[mask]) of refiner.py:332.
+ * ---------------------------------------------------------------------------------------- */
+size_t fd_refine_pack_workspace_bytes(int B, int H, int W);
+int fd_refine_pack(const float* disp0, const float* beam, const float* two_cha, const float* const inv_K[4],
+                   int B, int H, int W, int crop_y0, int crop_y1, int crop_x0, int crop_x1, float min_depth,
+                   float max_depth, float* const out[4], float* ratios, void* workspace, void* stream);
+size_t fd_masked_median_workspace_bytes(int B, int H, int W);
+int fd_masked_median(const float* x, const float* mask_src, int B, int H, int W, int y0, int y1, int x0,
+                     int x1, float scale, float* out, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Network operators (NHWC fp32).  Replace the ATen/cuDNN ops under networks/resnet_encoder.py,
@@ -226,7 +290,9 @@ int fd_mean_hw_bwd(const float* dy, float* dx, int B, int HW, int C, float scale
 
 /* torch.optim.Adam update on flat buffers (trainer.py:129): g is multiplied by grad_scale first.
  * state: 4 x int32 device words, state[0] = number of steps taken so far (incremented here, on
- * the device, so that a captured CUDA graph advances the bias correction on every replay). */
+ * the device, so that a captured CUDA graph advances the bias correction on every replay).
+ * lr < 0: the learning rate is read from state[3] (float bits) on the device instead, so that a learning
+ * rate schedule (StepLR, trainer.py:131-132, 266) reaches a captured graph. */
 int fd_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                  float beta2, float eps, int* state, float grad_scale, void* stream);
 

@@ -372,9 +372,89 @@ def cat_xy(depth: Tensor, inv_K: Tensor) -> Tensor:
 
 def siloss(pred: Tensor, gt: Tensor, thresh: float = 2.0, si_var: float = 0.3) -> Tensor:
     # refiner.py:557-563 (called with depth, inf_gdc at 678-688)
-    valid = ((gt > 0) * (abs(pred - gt) < thresh)).detach()
+    valid = ((gt > 1e-3) * (pred < 80) * (pred > 1e-3) * (abs(pred - gt) < thresh)).detach()
     d = torch.log(pred[valid]) - torch.log(gt[valid])
-    return torch.sqrt((d ** 2).mean() - si_var * (d.mean() ** 2))
+    return torch.sqrt((d ** 2).mean() - si_var * (d.mean() ** 2)) * 10.0
+
+
+CROP = (78, 190, 23, 617)      # refiner.py:330 (the 375x1242 Garg-like crop at 192x640)
+
+
+def pseudo3d_pack(disps: Dict, inputs: Dict, scales=(0, 1, 2, 3), min_depth=0.1, max_depth=100.0):
+    """refiner.py:316-346 with the default flags (refine_a0='true', catxy='true'): the 6-channel
+    pseudo-3D maps [scaled_disp(1), xyz(3), two_cha(2)] per scale, from the frozen stage-1 disparity
+    at scale 0.  Returns ({("disp", s): [B,6,h,w]}, ratios[s])."""
+    H, W = inputs[("color", 0, 0)].shape[-2:]
+    beam = inputs["4beam"]
+    two_cha = inputs["2channel"]
+    disp_0 = disps[("disp", 0)]
+    out, ratios = {}, []
+    for s in scales:
+        disp = disp_0
+        disp_0 = F.max_pool2d(disp_0, 2, ceil_mode=True)
+        disp640 = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+        depth = disp_to_depth(disp640, min_depth, max_depth)[1]
+        mask = beam > 0
+        crop = torch.zeros_like(mask)
+        crop[:, :, CROP[0]:CROP[1], CROP[2]:CROP[3]] = 1
+        mask = mask * crop
+        ratio = torch.median(beam[mask] * 100.0) / torch.median(depth[mask]).detach()
+        ratios.append(ratio)
+        depth = depth * ratio
+        scaled_disp = (F.interpolate(1 / depth, disp.shape[2:], mode="bilinear",
+                                     align_corners=False) - 0.01) / 9.9
+        if s != 0:
+            two_cha = F.max_pool2d(two_cha, 2, ceil_mode=True)
+        for _ in range(s):
+            depth = F.max_pool2d(depth, 2, ceil_mode=True)
+        xyz = cat_xy(depth, inputs[("inv_K", s)])
+        out[("disp", s)] = torch.cat([scaled_disp, xyz, two_cha], 1)
+    return out, ratios
+
+
+def refiner_process_batch(models: Dict[str, Dict[str, Tensor]], inputs: Dict, noise: Dict,
+                          num_layers: int = 18, training: bool = True, frame_ids=(0, -1, 1),
+                          scales=(0, 1, 2, 3), gdc_weight=0.008, gdc_thresh=2.0, si_var=0.3,
+                          smoothness=1e-3):
+    """Refiner.process_batch + compute_losses (refiner.py:299-378, 586-693), default flags: frozen
+    stage-1 encoder / beam encoder / depth decoder under no_grad (BatchNorm still in train mode --
+    run_epoch calls set_train(), refiner.py:268 -- and `depth(features)` WITHOUT beam features,
+    refine_depthnet_with_beam='false'), pseudo-3D pack, pose nets, the refine2d decoder
+    (road, catxy, deep; sigmoid since refine_offset is off), the same warp + photometric + smoothness
+    chain as stage 1, and the GDC-clone si-loss on scale 0 (x gdc_loss_weight x 4)."""
+    with torch.no_grad():
+        feats = resnet_encoder(models["encoder"], inputs[("color_aug", 0, 0)], num_layers, training)
+        beam = resnet_encoder(models["beam_encoder"], inputs["2channel"], num_layers, training)
+        coarse = depth_decoder(models["depth"], feats, beam_feats=None, scales=scales)
+        packed, ratios = pseudo3d_pack(coarse, inputs, scales)
+    outputs = {("pseudo3d", s): packed[("disp", s)] for s in scales}
+    outputs["ratios"] = torch.stack(ratios)
+    cam_T = {}
+    for f in frame_ids[1:]:
+        pair = (f, 0) if f < 0 else (0, f)
+        img = torch.cat([inputs[("color_aug", i, 0)] for i in pair], 1)
+        two = torch.cat([inputs[("2channel", i, 0)] for i in pair], 1)
+        pf = resnet_encoder(models["pose_encoder"], img, num_layers, training)
+        bf = resnet_encoder(models["beam_encoder_pose"], two, num_layers, training)
+        aa, tr = pose_decoder(models["pose"], pf[-1], bf[-1])
+        cam_T[f] = pose_matrix(aa[:, 0], tr[:, 0], invert=(f < 0))
+        outputs[("cam_T_cam", 0, f)] = cam_T[f]
+    disps = depth_decoder(models["refine2d_decoder"], feats, beam_feats=beam, depth_maps=packed,
+                          scales=scales, deep=True)
+    outputs.update(disps)
+    pl, o2 = photometric_chain(inputs, disps, cam_T, noise, frame_ids, scales, smoothness=smoothness,
+                               siloss=False)
+    outputs.update(o2)
+    H, W = inputs[("color", 0, 0)].shape[-2:]
+    losses = {"loss/gama1.0_scale%d" % s: pl["loss/%d" % s] for s in scales}
+    total = sum(pl["loss/%d" % s] for s in scales)
+    # refiner.py:678-688 (gdc_loss_only_on_scale_0 defaults to True: store_false flag)
+    d0 = F.interpolate(disps[("disp", 0)], [H, W], mode="bilinear", align_corners=False).squeeze()
+    depth0 = disp_to_depth(d0, 0.1, 100.0)[1]
+    gdc = siloss(depth0, inputs["inf_gdc"].squeeze(), gdc_thresh, si_var) * gdc_weight * 4.0
+    losses["loss/gdc_scale0"] = gdc
+    losses["loss"] = (total + gdc) / len(scales)
+    return outputs, losses
 
 
 # --------------------------------------------------------------------------

@@ -61,3 +61,12 @@ def rel_err(a, b) -> float:
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def coarse_disparity(B, H, W, seed=3):
+    """A smooth synthetic stage-1 disparity [B,1,H,W] in (0,1) for the pseudo-3D pack fixtures."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(B, 1, H // 8, W // 8, generator=g)
+    d = torch.sigmoid(4 * (F.interpolate(low, (H, W), mode="bilinear", align_corners=False) - 0.5) - 1.0)
+    return (d + 0.01 * torch.rand(B, 1, H, W, generator=g)).contiguous()

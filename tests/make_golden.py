@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import _refharness as RH            # noqa: E402
-from tests._util import GOLDEN, synth_weights   # noqa: E402
+from tests._util import GOLDEN, coarse_disparity, synth_weights   # noqa: E402
 from fusiondepth_b200 import synth              # noqa: E402
 
 torch.set_num_threads(8)
@@ -204,6 +204,114 @@ def gen_loss_chain(ns, B=2, H=96, W=160):
     print("loss_chain", {k: float(v) for k, v in losses.items()})
 
 
+def gen_refiner(B=2, H=192, W=640):
+    """Refiner.process_batch + backward (BASELINE config 5 semantics; the reference hard-codes 192x640 in
+    the GDC term and the 78:190 x 23:617 crop, so the fixture runs at that size with B=2)."""
+    ns = RH.load(with_refiner=True)
+    models = RH.make_models(ns, 18)
+    models["refine2d_decoder"] = RH.make_refine_decoder(ns, models["encoder"].num_ch_enc)
+    _load_weights(models, 4)
+    for m in models.values():
+        m.train()                                    # refiner.py:268 set_train() flips the frozen nets too
+    rf = RH.make_refiner(ns, models, B, H, W)
+    inputs = synth.make_refiner_batch(B, H, W, seed=6)
+    noise = inputs.pop("noise")
+    with RH.FixedNoise([noise[s] for s in range(4)]):
+        outputs, losses = rf.process_batch(dict(inputs))
+    losses["loss"].backward()
+    out = {}
+    for s in range(4):
+        d = outputs[("disp", s)].detach().numpy()
+        out["disp%d" % s] = d if s else d[:, :, ::4, ::4]
+        out["identity_selection%d_mean" % s] = outputs["identity_selection/%d" % s].mean().numpy()
+    for f in (-1, 1):
+        out["cam_T_cam%d" % f] = outputs[("cam_T_cam", 0, f)].detach().numpy()
+    for k, v in losses.items():
+        out["loss:" + k] = v.detach().numpy()
+    for k, p in models["refine2d_decoder"].named_parameters():
+        out["gnorm:" + k] = p.grad.double().norm().numpy()
+    out["grad:decoder.0.0"] = models["refine2d_decoder"].decoder[0][0].conv.conv.weight.grad.numpy()[:4]
+    out["grad:decoder.13"] = models["refine2d_decoder"].decoder[13].conv.weight.grad.numpy()
+    for k, b in models["encoder"].named_buffers():
+        if k.endswith("running_mean"):
+            out["buf:encoder/" + k] = b.double().norm().numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "refiner.npz"), **out)
+    print("refiner", {k: float(v) for k, v in losses.items()})
+
+    # the pseudo-3D pack alone (refiner.py:316-346) on a synthetic coarse disparity: stored whole
+    Bp = 2
+    inputs = synth.make_refiner_batch(Bp, H, W, seed=8)
+    coarse = coarse_disparity(Bp, H, W, seed=3)
+    rf2 = RH.make_refiner(ns, models, Bp, H, W)
+
+    class _Frozen:                                        # stands in for the three frozen networks
+        def __init__(self, ret):
+            self.ret = ret
+
+        def __call__(self, *a, **k):
+            return self.ret
+    cap = {}
+
+    class _Capture:
+        def __call__(self, features, beam_features=None, depth_maps=None, tanh=False):
+            for s in range(4):
+                cap[s] = depth_maps[("disp", s)].clone()
+            raise StopIteration
+    rf2.models = dict(models)
+    rf2.models["encoder"] = _Frozen(None)
+    rf2.models["beam_encoder"] = _Frozen(None)
+    rf2.models["depth"] = _Frozen({("disp", 0): coarse})
+    rf2.models["refine2d_decoder"] = _Capture()
+    rf2.use_pose_net = False
+    try:
+        rf2.process_batch(dict((k, v) for k, v in inputs.items() if k != "noise"))
+    except StopIteration:
+        pass
+    pk = {}
+    for s in range(4):
+        pk["pack%d" % s] = cap[s].numpy() if s else cap[s].numpy()[:, :, ::2, ::2]
+    np.savez_compressed(os.path.join(GOLDEN, "refiner_pack.npz"), **pk)
+    print("refiner pack", [tuple(cap[s].shape) for s in range(4)])
+
+
+def gen_r50_train(B=2, H=64, W=96):
+    """ResNet-50 (Bottleneck) encoder + beam encoder + decoder in TRAIN mode with backward: a scalar loss
+    over the four disparities, feature maps, parameter-gradient norms and BN running statistics."""
+    ns = RH.load()
+    N = ns.networks
+    enc, benc = N.ResnetEncoder(50, False), N.ResnetEncoder(50, False, beam_encoder=True)
+    dec = N.DepthDecoder(enc.num_ch_enc, [0, 1, 2, 3])
+    mods = {"enc": enc, "benc": benc, "dec": dec}
+    for i, (k, m) in enumerate(sorted(mods.items())):
+        m.load_state_dict(synth_weights(m.state_dict(), 5000 + i))
+        m.train()
+    g = torch.Generator().manual_seed(21)
+    rgb = torch.rand(B, 3, H, W, generator=g)
+    two = torch.rand(B, 2, H, W, generator=g) * (torch.rand(B, 1, H, W, generator=g) < 0.1)
+    wts = [torch.randn(B, 1, H >> s, W >> s, generator=g) for s in range(4)]
+    feats = enc(rgb)
+    feats = [f for f in feats]
+    d = dec(feats, beam_features=benc(two))
+    loss = sum((d[("disp", s)] * wts[s]).mean() for s in range(4))
+    loss.backward()
+    out = {"rgb": rgb.numpy(), "two": two.numpy(), "loss": loss.detach().numpy()}
+    for s in range(4):
+        out["w%d" % s] = wts[s].numpy()
+        out["disp%d" % s] = d[("disp", s)].detach().numpy()
+    out["feat4"] = feats[4].detach().numpy()
+    for name, m in mods.items():
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                out["gnorm:%s/%s" % (name, k)] = p.grad.double().norm().numpy()
+        for k, b in m.named_buffers():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                out["buf:%s/%s" % (name, k)] = b.double().norm().numpy()
+    out["grad:enc/layer1.0.conv1"] = enc.encoder.layer1[0].conv1.weight.grad.numpy()
+    out["grad:enc/layer4.2.conv3"] = enc.encoder.layer4[2].conv3.weight.grad.numpy()[:16]
+    np.savez_compressed(os.path.join(GOLDEN, "r50_train.npz"), **out)
+    print("r50 train", float(loss))
+
+
 def gen_state_dict_keys(ns):
     """key -> shape of every network variant the drivers build, from the REFERENCE modules."""
     import json
@@ -228,7 +336,11 @@ if __name__ == "__main__":
     assert RH.available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN, exist_ok=True)
     ns = RH.load()
-    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss", "keys"]
+    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss", "keys", "refiner", "r50"]
+    if "refiner" in which:
+        gen_refiner()
+    if "r50" in which:
+        gen_r50_train()
     if "keys" in which:
         gen_state_dict_keys(ns)
     if "lidar" in which:

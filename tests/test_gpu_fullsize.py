@@ -1,0 +1,104 @@
+"""Parity at the BENCH configuration itself: BASELINE.json config 2's micro-batch (6 x 192 x 640,
+ResNet-18) -- the fused loss chain and the whole process_batch + backward against the CPU oracle on
+identical seeded inputs, values not just invariants.  Tolerance: 1e-4 relative fp32 on loss / disp /
+depth tensors (north_star); gradients as in the small-size tests (argmin ties + fp32 atomics)."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import clone_sd, rel_err, synth_weights
+from fusiondepth_b200 import synth
+from oracle import step_oracle as SO
+
+pytestmark = pytest.mark.gpu
+B, H, W = 6, 192, 640
+
+
+def test_loss_chain_bench_size_vs_oracle(cuda):
+    from tests.test_gpu_photoloss import _run_cuda
+    inputs = synth.make_batch(B, H, W, seed=31, mode="coherent")
+    noise = inputs.pop("noise")
+    g = torch.Generator().manual_seed(H)
+    disps = {("disp", s): torch.sigmoid(torch.randn(B, 1, H >> s, W >> s, generator=g) * 0.5 - 1)
+             for s in range(4)}
+    Ts = {f: SO.pose_matrix(0.01 * torch.randn(B, 1, 3, generator=g), 0.05 * torch.randn(B, 1, 3, generator=g),
+                            f < 0) for f in (-1, 1)}
+    with torch.no_grad():
+        up = torch.nn.functional.interpolate(disps[("disp", 0)], [H, W], mode="bilinear", align_corners=False)
+        dep = 26.0 / (0.01 + 9.99 * up)
+        mask = (torch.rand(B, 1, H, W, generator=g) < 0.03).float()
+        inputs["4beam"] = mask * (dep + (torch.rand(B, 1, H, W, generator=g) - 0.5) * 3.0) / 100.0
+    od = {k: v.clone().requires_grad_(True) for k, v in disps.items()}
+    oT = {f: Ts[f].clone().requires_grad_(True) for f in Ts}
+    ol, oo = SO.photometric_chain(inputs, od, oT, noise)
+    ol["loss"].backward()
+    losses, outputs, leaves = _run_cuda(inputs, noise, disps, Ts)
+    for k in ol:
+        assert rel_err(losses[k].cpu(), ol[k].detach()) < 1e-4, (k, float(losses[k]), float(ol[k]))
+    for s in range(4):
+        assert rel_err(outputs[("depth", 0, s)].cpu(), oo[("depth", 0, s)].detach()) < 1e-4
+        assert rel_err(outputs["to_optimise/%d" % s].cpu(), oo["to_optimise/%d" % s].detach()) < 2e-4
+        for f in (-1, 1):
+            assert rel_err(outputs[("color", f, s)].cpu(), oo[("color", f, s)].detach()) < 2e-4
+        mism = (outputs["identity_selection/%d" % s].cpu() != oo["identity_selection/%d" % s]).float().mean()
+        assert float(mism) < 1e-3, (s, float(mism))
+        assert rel_err(leaves["disp%d" % s].grad.cpu(), od[("disp", s)].grad) < 2e-3, s
+    for f in (-1, 1):
+        assert rel_err(leaves["T%d" % f].grad.cpu(), oT[f].grad) < 2e-3, f
+
+
+def test_process_batch_bench_size_vs_oracle(cuda):
+    """The 20x12-tile grid, the M = 46 080 ... 737 280 layer shapes and the wide-N conv tiles the bench
+    runs: losses, disparities, depths, poses < 1e-4; BN batch statistics; full gradient tensors."""
+    from fusiondepth_b200 import training
+    models = training.build_models(18, "cuda")
+    sds = {}
+    for i, (name, m) in enumerate(sorted(models.items())):
+        sds[name] = synth_weights(m.state_dict(), 700 + i)
+        m.load_state_dict(sds[name])
+        m.train()
+    osd = {k: clone_sd(v, requires_grad=True) for k, v in sds.items()}
+    inputs = synth.make_batch(B, H, W, seed=41, mode="coherent", lidar_density=0.03)
+    noise = inputs.pop("noise")
+    oo, ol = SO.process_batch(osd, inputs, noise, 18, training=True)
+    ol["loss"].backward()
+    outputs, losses = training.process_batch(models, synth.to_device(inputs, "cuda"),
+                                             {s: t.cuda() for s, t in noise.items()}, None, materialize=True)
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+    for k in ol:
+        assert rel_err(losses[k].detach().cpu(), ol[k].detach()) < 1e-4, (k, float(losses[k]), float(ol[k]))
+    for s in range(4):
+        assert rel_err(outputs[("disp", s)].detach().cpu(), oo[("disp", s)].detach()) < 1e-4, s
+        assert rel_err(outputs[("depth", 0, s)].detach().cpu(), oo[("depth", 0, s)].detach()) < 1e-4, s
+    for f in (-1, 1):
+        assert rel_err(outputs[("cam_T_cam", 0, f)].detach().cpu(), oo[("cam_T_cam", 0, f)].detach()) < 1e-5
+        assert rel_err(outputs[("color", f, 0)].detach().cpu(), oo[("color", f, 0)].detach()) < 2e-4
+    for name in models:
+        for k, b in models[name].named_buffers():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                assert rel_err(b.cpu(), osd[name][k]) < 1e-4, (name, k)
+    # full gradient tensors from every network, early and late layers
+    checked = 0
+    for name, key in (("depth", "decoder.0.conv.conv.weight"), ("depth", "decoder.9.conv.conv.weight"),
+                      ("depth", "decoder.13.conv.weight"), ("pose", "net.3.weight"), ("pose", "net.0.weight"),
+                      ("encoder", "encoder.conv1.weight"), ("encoder", "encoder.layer1.0.conv1.weight"),
+                      ("encoder", "encoder.layer4.1.conv2.weight"), ("encoder", "encoder.layer2.0.bn1.weight"),
+                      ("beam_encoder", "encoder.layer3.0.downsample.0.weight"),
+                      ("pose_encoder", "encoder.layer1.1.conv2.weight"),
+                      ("beam_encoder_pose", "encoder.conv1.weight")):
+        p = dict(models[name].named_parameters())[key]
+        assert rel_err(p.grad.cpu(), osd[name][key].grad) < 5e-3, (name, key)
+        checked += 1
+    # and every parameter-gradient norm
+    bad = []
+    for name in models:
+        for k, p in models[name].named_parameters():
+            og = osd[name][k].grad
+            if og is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, (name, k)
+                continue
+            got, want = float(p.grad.double().norm()), float(og.double().norm())
+            if abs(got - want) > 5e-3 * want + 1e-9:
+                bad.append((name, k, got, want))
+    assert checked == 12 and not bad, bad[:10]

@@ -27,7 +27,7 @@ def test_dropin_shims_resolve():
             sys.modules.pop(m, None)
         import layers as L
         import networks as N
-        assert L.F is torch.nn.functional and L.nn is torch.nn
+        assert L.F.conv2d is torch.nn.functional.conv2d and L.nn is torch.nn
         assert N.ResnetEncoder.__module__.startswith("fusiondepth_b200")
         assert {"ResnetEncoder", "DepthDecoder", "PoseDecoder", "PoseCNN"} <= set(dir(N))
     finally:
@@ -60,23 +60,17 @@ def test_state_dict_contract():
         N.ResnetEncoder(19, False)
 
 
-def test_geometry_layers_match_oracle():
+def test_torch_composed_layers_match_oracle():
+    """The functions of the surface that are plain tensor compositions (no kernel needed) on CPU; the
+    modules with kernels behind them are checked on the GPU (tests/test_gpu_geometry.py)."""
     from fusiondepth_b200 import layers as L
     g = torch.Generator().manual_seed(0)
     B, H, W = 2, 16, 24
     depth = 0.5 + torch.rand(B, 1, H, W, generator=g) * 10
-    K = torch.tensor([[0.58 * W, 0, 0.5 * W, 0], [0, 1.92 * H, 0.5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1.]]).repeat(B, 1, 1)
-    invK = torch.linalg.pinv(K)
     aa, tt = 0.02 * torch.randn(B, 1, 3, generator=g), 0.1 * torch.randn(B, 1, 3, generator=g)
     for inv in (False, True):
         assert rel_err(L.transformation_from_parameters(aa, tt, inv), SO.pose_matrix(aa, tt, inv)) < 1e-6
-    T = L.transformation_from_parameters(aa, tt, False)
-    pts = L.BackprojectDepth(B, H, W)(depth, invK)
-    assert rel_err(pts, SO.backproject(depth, invK)) < 1e-6
-    assert rel_err(L.Project3D(B, H, W)(pts, K, T), SO.project(pts, K, T, H, W)) < 1e-6
-    assert rel_err(L.Cat_xy(B, H, W)(depth, invK), SO.cat_xy(depth, invK)) < 1e-6
-    x, y = torch.rand(B, 3, H, W, generator=g), torch.rand(B, 3, H, W, generator=g)
-    assert rel_err(L.SSIM()(x, y), SO.ssim(x, y)) < 1e-6
+    x = torch.rand(B, 3, H, W, generator=g)
     disp = torch.rand(B, 1, H, W, generator=g)
     assert rel_err(L.get_smooth_loss(disp, x), SO.smooth_loss(disp, x)) < 1e-6
     sd, d = L.disp_to_depth(disp, 0.1, 100.0)
@@ -84,6 +78,14 @@ def test_geometry_layers_match_oracle():
     assert torch.equal(sd, osd) and torch.equal(d, od)
     errs = L.compute_depth_errors(depth, depth * 1.1)
     assert abs(float(errs[0]) - 0.1) < 1e-5 and float(errs[4]) == 1.0
-    # batch-size mismatch surfaces as a RuntimeError, like the reference
-    with __import__("pytest").raises(RuntimeError):
-        L.BackprojectDepth(B + 1, H, W)(depth, invK)
+    # modules with kernels behind them refuse CPU tensors (no CPU fallback)
+    from fusiondepth_b200 import _lib
+    K = torch.eye(4).repeat(B, 1, 1)
+    with __import__("pytest").raises(_lib.FusionDepthLibraryError):
+        L.BackprojectDepth(B, H, W)(depth, K)
+    with __import__("pytest").raises(_lib.FusionDepthLibraryError):
+        L.SSIM()(x, x)
+    # layers.F is torch.nn.functional for everything off the hot path
+    assert L.F.relu is torch.nn.functional.relu and L.F.max_pool2d is torch.nn.functional.max_pool2d
+    y = L.F.interpolate(disp, [2 * H, 2 * W], mode="bilinear", align_corners=False)      # CPU: torch's own
+    assert torch.equal(y, torch.nn.functional.interpolate(disp, [2 * H, 2 * W], mode="bilinear", align_corners=False))

@@ -166,3 +166,87 @@ def test_adam_oracle_matches_torch():
         opt.step()
         SO.adam_step([p], [gr], [m], [v], step, 1e-3)
     assert rel_err(p, ref.detach()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ refiner
+def _refiner_sds(seed=4):
+    tmpl = {
+        "encoder": networks.ResnetEncoder(18, False),
+        "beam_encoder": networks.ResnetEncoder(18, False, beam_encoder=True),
+        "beam_encoder_pose": networks.ResnetEncoder(18, False, num_input_images=2, beam_encoder=True),
+        "depth": networks.DepthDecoder(np.array([64, 64, 128, 256, 512]), [0, 1, 2, 3]),
+        "pose_encoder": networks.ResnetEncoder(18, False, num_input_images=2),
+        "pose": networks.PoseDecoder(np.array([64, 64, 128, 256, 512]), 1, 2),
+        "refine2d_decoder": networks.DepthDecoder(np.array([64, 64, 128, 256, 512]), [0, 1, 2, 3],
+                                                  road=True, catxy=True, deep=True),
+    }
+    return {name: synth_weights(m.state_dict(), seed * 100 + i)
+            for i, (name, m) in enumerate(sorted(tmpl.items()))}
+
+
+def test_refiner_pack_oracle_matches_reference_fixture():
+    """refiner.py:316-346 (median rescale, cumulative max-pools, Cat_xy) on a synthetic coarse disparity."""
+    from tests._util import coarse_disparity
+    g = _g("refiner_pack")
+    inputs = synth.make_refiner_batch(2, 192, 640, seed=8)
+    packed, _ = SO.pseudo3d_pack({("disp", 0): coarse_disparity(2, 192, 640, seed=3)}, inputs)
+    for s in range(4):
+        got = packed[("disp", s)] if s else packed[("disp", s)][:, :, ::2, ::2]
+        assert torch.equal(got, torch.from_numpy(g["pack%d" % s])), s
+
+
+def test_refiner_oracle_matches_reference_fixture():
+    """Refiner.process_batch + backward at 2x192x640 (BASELINE config 5 semantics)."""
+    g = _g("refiner")
+    sds = {k: clone_sd(v, requires_grad=(k == "refine2d_decoder")) for k, v in _refiner_sds().items()}
+    inputs = synth.make_refiner_batch(2, 192, 640, seed=6)
+    noise = inputs.pop("noise")
+    outputs, losses = SO.refiner_process_batch(sds, inputs, noise, 18, training=True)
+    losses["loss"].backward()
+    for k in losses:
+        assert rel_err(losses[k].detach(), g["loss:" + k]) < 1e-5, (k, float(losses[k]), float(g["loss:" + k]))
+    for s in range(4):
+        d = outputs[("disp", s)].detach()
+        assert rel_err(d if s else d[:, :, ::4, ::4], g["disp%d" % s]) < 1e-5, s
+        assert abs(float(outputs["identity_selection/%d" % s].mean()) - float(g["identity_selection%d_mean" % s])) < 1e-4
+    for f in (-1, 1):
+        assert rel_err(outputs[("cam_T_cam", 0, f)].detach(), g["cam_T_cam%d" % f]) < 1e-5
+    n = 0
+    for key in g.files:
+        if key.startswith("gnorm:"):
+            got = float(sds["refine2d_decoder"][key[6:]].grad.double().norm())
+            assert abs(got - float(g[key])) < 1e-3 * float(g[key]) + 1e-12, key
+            n += 1
+        elif key.startswith("buf:encoder/"):
+            got = float(sds["encoder"][key[12:]].double().norm())
+            assert abs(got - float(g[key])) < 1e-5 * float(g[key]), key
+    assert n == 48
+    assert rel_err(sds["refine2d_decoder"]["decoder.0.0.conv.conv.weight"].grad[:4], g["grad:decoder.0.0"]) < 1e-3
+    assert rel_err(sds["refine2d_decoder"]["decoder.13.conv.weight"].grad, g["grad:decoder.13"]) < 1e-3
+
+
+def test_r50_train_oracle_matches_reference_fixture():
+    """Bottleneck (ResNet-50) train-mode forward + backward vs the reference fixture."""
+    g = _g("r50_train")
+    ch = np.array([64, 256, 512, 1024, 2048])
+    tmpl = {"enc": networks.ResnetEncoder(50, False), "benc": networks.ResnetEncoder(50, False, beam_encoder=True),
+            "dec": networks.DepthDecoder(ch, [0, 1, 2, 3])}
+    sds = {k: clone_sd(synth_weights(m.state_dict(), 5000 + i), requires_grad=True)
+           for i, (k, m) in enumerate(sorted(tmpl.items()))}
+    rgb, two = torch.from_numpy(g["rgb"]), torch.from_numpy(g["two"])
+    feats = SO.resnet_encoder(sds["enc"], rgb, 50, True)
+    d = SO.depth_decoder(sds["dec"], feats, beam_feats=SO.resnet_encoder(sds["benc"], two, 50, True))
+    loss = sum((d[("disp", s)] * torch.from_numpy(g["w%d" % s])).mean() for s in range(4))
+    loss.backward()
+    assert rel_err(loss.detach(), g["loss"]) < 1e-5
+    for s in range(4):
+        assert rel_err(d[("disp", s)].detach(), g["disp%d" % s]) < 1e-5
+    assert rel_err(feats[4].detach(), g["feat4"]) < 1e-5
+    n = 0
+    for key in g.files:
+        if key.startswith("gnorm:"):
+            name, pk = key[6:].split("/", 1)
+            got = float(sds[name][pk].grad.double().norm())
+            assert abs(got - float(g[key])) < 1e-3 * float(g[key]) + 1e-12, key
+            n += 1
+    assert n > 300
