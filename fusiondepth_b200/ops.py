@@ -372,7 +372,8 @@ def zero_segment(B, C, H, W, device):
     key = (B, C, H, W, str(device))
     z = _ZERO_SEGMENTS.get(key)
     if z is None:
-        z = _ZERO_SEGMENTS[key] = torch.zeros((B, C, H, W), device=device, dtype=torch.float32, memory_format=CL)
+        z = _ZERO_SEGMENTS[key] = torch.zeros((B, C, H, W), device=device, dtype=torch.float32).contiguous(
+            memory_format=CL)
     return z
 
 

@@ -1,4 +1,4 @@
-"""Summarises tests/prof_timeline.py output: step span, per-stream busy time, concurrency histogram,
+"""Summarises tools/prof_timeline.py output: step span, per-stream busy time, concurrency histogram,
 time by kernel family on the whole device, and the idle gaps.
 usage: python profiles/timeline_report.py gpurun_out/timeline.csv"""
 import csv, re, sys

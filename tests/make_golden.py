@@ -274,7 +274,7 @@ def gen_refiner(B=2, H=192, W=640):
     print("refiner pack", [tuple(cap[s].shape) for s in range(4)])
 
 
-def gen_r50_train(B=2, H=64, W=96):
+def gen_r50_train(B=2, H=96, W=160):
     """ResNet-50 (Bottleneck) encoder + beam encoder + decoder in TRAIN mode with backward: a scalar loss
     over the four disparities, feature maps, parameter-gradient norms and BN running statistics."""
     ns = RH.load()

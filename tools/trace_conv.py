@@ -1,5 +1,5 @@
 """Timing experiment (not a test): per-role clock64() trace of CTA (0,0) of one tensor-core conv launch.
-usage: FD_TC2_FLAGS=<flags|128> python tests/trace_conv.py  ->  per-k-block intervals of loader / splitter / MMA"""
+usage: FD_TC2_FLAGS=<flags|128> python tools/trace_conv.py  ->  per-k-block intervals of loader / splitter / MMA"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes
