@@ -162,7 +162,7 @@ def reference_stepper(device, allow_tf32=None):
 
         def step(batch, noise):
             optim.zero_grad()
-            with RH.FixedNoise([noise[s] for s in range(4)]):
+            with RH.FixedNoise([noise[s] for s in range(4)], cpu=(str(device) == "cpu")):
                 _, losses = drv.process_batch(dict(batch))
             (losses["loss"] / ACCUM).backward()
             optim.step()
@@ -369,7 +369,7 @@ def cpu_baseline_leg(sds0, batches, noises):
                RH.make_trainer(ns, models, MICRO_B, H, W, batch_size_flag=MICRO_B * ACCUM))
 
         def micro(b, n):
-            with RH.FixedNoise([n[s] for s in range(4)]):
+            with RH.FixedNoise([n[s] for s in range(4)], cpu=True):
                 _, l = drv.process_batch(dict(b))
             (l["loss"] / ACCUM).backward()
             return float(l["loss"])

@@ -100,6 +100,7 @@ _SIGNATURES = {
     "fd_conv2d_c16_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_c16_dgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fd_conv2d_c16_wgrad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "fd_bn_workspace_bytes": (c_size_t, [_I]),
     "fd_bn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "fd_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "fd_maxpool3x3s2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),

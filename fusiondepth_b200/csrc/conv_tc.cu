@@ -683,6 +683,23 @@ static bool tc_use_v2() {
   return v == 1;
 }
 
+static bool tc_use_v3() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FD_CONV_TC3");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+// conv_tc3 (patch variant) where it applies, else conv_tc2
+static int tc_v2_or_v3(const TcArgs& a, int mode, cudaStream_t st) {
+  if (tc_use_v3() && !(a.flags & ~0x800)) {
+    int rc = fd::conv_tc3_dispatch(a, mode, st);
+    if (rc >= 0) return rc;
+  }
+  return fd::conv_tc2_dispatch(a, mode, st);
+}
+
 extern "C" {
 
 int fd_conv2d_tc_supported(int Cin, int Cout) { return (Cin % 32 == 0) && (Cout % 16 == 0); }
@@ -739,7 +756,7 @@ int fd_conv2d_fwd_tc_stats(const float* x, const float* w, const float* w_lo, co
   a.M = (long)B * a.Ho * a.Wo;
   a.K = KH * KW * Cin;
   a.flags = tc2_flags();
-  if (tc_use_v2()) return fd::conv_tc2_dispatch(a, 0, (cudaStream_t)stream);
+  if (tc_use_v2()) return tc_v2_or_v3(a, 0, (cudaStream_t)stream);
   return dispatch_tc<0>(a, (cudaStream_t)stream);
 }
 
@@ -759,7 +776,7 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
   a.M = (long)B * H * W;
   a.K = KH * KW * Cout;
   a.flags = tc2_flags();
-  if (tc_use_v2()) return fd::conv_tc2_dispatch(a, 1, (cudaStream_t)stream);
+  if (tc_use_v2()) return tc_v2_or_v3(a, 1, (cudaStream_t)stream);
   return dispatch_tc<1>(a, (cudaStream_t)stream);
 }
 

@@ -57,7 +57,8 @@ struct Cfg2 {
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(NTHREADS2, 1)
-conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo) {
+conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo,
+                const __grid_constant__ CUtensorMap tm_y) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -286,7 +287,7 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           if (i < nacc) {
             const int col = single ? (C::PAIR ? BN + 2 * i * BN : (1 + i) * BN)
                                    : (i == nacc - 1 ? 0 : (C::PAIR ? BN + i * BN : (1 + i) * BN));
-            tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);
+            if (!(a.flags & 0x400)) tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);   // 0x400: timing experiment
           }
         }
         tmem_wait_ld();
@@ -323,16 +324,29 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(BN + ch)), "f"(s2[0]) : "memory");
         }
       }
-      if (m < a.M && n0 + c < a.N) {
+      if (BN >= 32) {
+        // Stage the tile in shared memory (the pipeline stages are all consumed by now) and let TMA write it:
+        // one row per lane, the direct float4 stores reach global memory as 32 scattered 16-byte pieces per
+        // instruction (rows are N*4 bytes apart) -- measured 23 % of the layer-1 kernel.
         float o[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float bv = a.bias ? a.bias[n0 + c + e] : 0.f;
-          o[e] = act_fn(acc[e] + bv, a.act);
-        }
+        bias_act16(acc, a.bias ? a.bias + n0 + c : nullptr, a.act, o);
+        stage_out16(base, row, c, o);
+      } else if (m < a.M && n0 + c < a.N) {
+        float o[16];
+        bias_act16(acc, a.bias ? a.bias + n0 + c : nullptr, a.act, o);
         float4* dst = reinterpret_cast<float4*>(a.y + m * a.N + n0 + c);
 #pragma unroll
         for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+      }
+    }
+    if (BN >= 32) {
+      fence_async_proxy();                                    // generic-proxy writes -> visible to the TMA unit
+      asm volatile("bar.sync 2, %0;" ::"n"(NSPLIT2) : "memory");
+      if (warp == NLOADW2 && elect_one() && !(a.flags & 0x200)) {
+#pragma unroll
+        for (int blk = 0; blk < BN / 32; ++blk)
+          if (n0 + 32 * blk < a.N) tma_store_2d(&tm_y, base + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, (int)m0);
+        tma_store_commit_wait();                              // shared memory is read before the CTA retires
       }
     }
     if (a.stats) {
@@ -451,15 +465,20 @@ int launch_tc2(const TcArgs& a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_map_2d(&twl, a.wlo, a.N, a.K, BN);
   if (rc) return rc;
+  CUtensorMap ty = tw;
+  if (BN >= 32) {
+    rc = make_map_2d(&ty, a.y, a.M, a.N, BM);
+    if (rc) return rc;
+  }
   dim3 grid(fd::cdiv(a.M, BM), fd::cdiv(a.N, BN));
-  conv_tc2_kernel<BN, MODE><<<grid, NTHREADS2, C::SMEM, st>>>(a, tw, twl);
+  conv_tc2_kernel<BN, MODE><<<grid, NTHREADS2, C::SMEM, st>>>(a, tw, twl, ty);
   FD_CHECK_LAUNCH();
   return 0;
 }
 
 template <int MODE>
 int dispatch_tc2(const TcArgs& a, cudaStream_t st) {
-  FD_REQUIRE((((uintptr_t)a.w | (uintptr_t)a.wlo | (uintptr_t)a.x) & 15) == 0,
+  FD_REQUIRE((((uintptr_t)a.w | (uintptr_t)a.wlo | (uintptr_t)a.x | (uintptr_t)a.y) & 15) == 0,
              "conv_tc2: operands must be 16-byte aligned");
   FD_REQUIRE(a.M < (1L << 31) && a.KH <= 8 && a.KW <= 8, "conv_tc2: problem too large (M=%ld, %dx%d)", a.M,
              a.KH, a.KW);

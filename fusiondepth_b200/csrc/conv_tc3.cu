@@ -1,0 +1,487 @@
+// Implicit-GEMM convolution (forward / data gradient, stride 1) on tcgen05 -- the "patch" variant of
+// conv_tc2.cu.  Same contract and numerics (3xTF32, A operand in tensor memory, accumulator rotation), but
+// it moves 2-3x fewer bytes from L2 to the SM:
+//
+//   * conv_tc2 gathers the [128 px x 32 ch] im2col tile once PER TAP (9 x 16 KB per 32-channel chunk for
+//     a 3x3) and fetches W and W_lo for every k-block.  ncu: 210 MB of L2->SM traffic per layer-1 launch
+//     against 23.7 MB of tensors -- at ~5 TB/s that IS the launch time: the L2 slices deliver ~6300 B/clk
+//     chip-wide (B300_MICROARCH.md, "LTS throughput cap"), i.e. ~43 B/clk per SM when all 148 pull, and a
+//     BN=64 k-block needs 32 KB = 770 clk of L2 time against 384 clk of MMAs.
+//   * Here the input pixels a tile needs for ALL taps of a 32-channel chunk -- a contiguous raster range of
+//     128 + (KH-1)*Wg + KW pixels, since consecutive output pixels read consecutive input pixels at stride 1 --
+//     are fetched ONCE by TMA ([pixels x 32 ch] boxes, SWIZZLE_128B, out-of-range rows zero-filled) into a
+//     double-buffered "patch"; the splitter warps read tap (kh,kw) of tile row r from patch row
+//     r0[r] + kh*Wg + kw.  W_lo = W - tf32(W) is computed in shared memory by four otherwise idle warps
+//     instead of being fetched.  Per k-block (BN=64, Wg=160): 6.4 KB of patch + 8 KB of W = 14.4 KB.
+//
+// Roles (480 threads, one CTA per SM):
+//   warps 0-3   weight splitters   W tile (TMA) -> W_lo tile next to it, fence.proxy.async, `wready`
+//   warps 4-11  A splitters        two groups on alternate k-blocks: patch row -> registers -> A / A_lo into the
+//                                  TMEM ring (tcgen05.st); then the epilogue (shared with conv_tc2's layout)
+//   warp 12     MMA issue          tcgen05.mma kind::tf32, A from TMEM, B = [W ; W_lo] from shared memory
+//   warp 13     W tiles by TMA     one k-block per stage
+//   warp 14     patches by TMA     one 32-channel chunk per buffer, a whole chunk ahead
+//
+// k-block order: chunk-major (c0 outer, taps inner), W tile column = tap*Cg + c0.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int T3_WSPLITW = 4, T3_ASPLITW = 8;
+constexpr int T3_MMA_WARP = T3_WSPLITW + T3_ASPLITW;        // 12
+constexpr int T3_WTMA_WARP = T3_MMA_WARP + 1;               // 13
+constexpr int T3_PTMA_WARP = T3_MMA_WARP + 2;               // 14
+constexpr int T3_NTHREADS = (T3_PTMA_WARP + 1) * 32;        // 480
+constexpr int PBOX = 64;                                    // patch rows per TMA box
+
+template <int BN>
+struct Cfg3 {
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int WSTAGE = 2 * B_TILE;                             // [W ; W_lo]
+  static constexpr int STAGES = BN == 128 ? 3 : 4;
+  static constexpr int PROWS = BN == 128 ? 384 : 512;                   // rows per patch buffer
+  static constexpr int PATCH = PROWS * 128;
+  static constexpr int TST = BN == 128 ? 2 : (BN == 64 ? 3 : 4);        // TMEM A-ring slots
+  static constexpr int ACC0 = TST * 64;
+  static constexpr bool PAIR = BN <= 64;
+  static constexpr int NMAIN_ = PAIR ? (512 - ACC0 - BN) / (2 * BN) : (512 - ACC0) / BN - 1;
+  static constexpr int NMAIN = NMAIN_ > 7 ? 7 : NMAIN_;
+  static constexpr int SMEM = 2 * PATCH + STAGES * WSTAGE + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row table*/ +
+                              1024 /*CTA channel sums*/;
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(T3_NTHREADS, 1)
+conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                const __grid_constant__ CUtensorMap tm_y) {
+  using C = Cfg3<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto patch = [&](int b) { return base + (uint32_t)b * C::PATCH; };
+  const uint32_t wbase = base + 2u * C::PATCH;
+  auto b_raw = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE; };
+  auto b_lo = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE + C::B_TILE; };
+  const uint32_t bars = wbase + C::STAGES * C::WSTAGE;
+  auto wland_bar = [&](int s) { return bars + 8u * s; };                        // W tile landed (TMA tx)
+  auto wready_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };         // W_lo written
+  auto wfree_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };      // MMAs done with the stage
+  auto tfull_bar = [&](int t) { return bars + 8u * (3 * C::STAGES + t); };
+  auto tfree_bar = [&](int t) { return bars + 8u * (3 * C::STAGES + C::TST + t); };
+  auto pfull_bar = [&](int b) { return bars + 8u * (3 * C::STAGES + 2 * C::TST + b); };
+  auto pfree_bar = [&](int b) { return bars + 8u * (3 * C::STAGES + 2 * C::TST + 2 + b); };
+  const uint32_t acc_bar = bars + 8u * (3 * C::STAGES + 2 * C::TST + 4);
+  const uint32_t tmem_slot = acc_bar + 8u;
+  const uint32_t pinfo = acc_bar + 16u;                   // [0] patch start (pixel index), [1] patch rows needed
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Tiles never cross an image: tile t of image b covers output pixels [t*128, t*128+128) of that image.  (A
+  // tile that crossed into the next image of a pad-0 layer would need the (Hg-Ho)*Wg pixels in between too.)
+  const int HoWo = a.Ho * a.Wo;
+  const int tpi = (HoWo + BM - 1) / BM;
+  const int img = (int)blockIdx.x / tpi, r0 = ((int)blockIdx.x - img * tpi) * BM;
+  const long m0 = (long)img * HoWo + r0;
+  const int rows_valid = HoWo - r0 < BM ? HoWo - r0 : BM;
+  const int n0 = blockIdx.y * BN;
+  const int taps = a.KH * a.KW;
+  const int nchunk = a.Cg / BK;
+  const int nk = taps * nchunk;
+  const int span = (a.KH - 1) * a.Wg + (a.KW - 1);        // largest tap shift
+
+  // Row table: tile row r -> (pixel index of its tap-(0,0) source, valid-tap mask); per-warp min / max of the
+  // pixel index in pinfo[0..3] / pinfo[4..7]
+  const uint32_t tab_lin = bars + 512u, tab_mask = tab_lin + 4u * BM;
+  const uint32_t cta_sums = tab_mask + 4u * BM;            // [2][BN] floats, only with a.stats
+  if (a.stats && tid >= BM && tid < BM + 2 * BN)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(tid - BM)), "f"(0.f) : "memory");
+  if (tid < BM) {
+    int lin = 0;
+    uint32_t mask = 0;
+    const bool valid = tid < rows_valid;
+    if (valid) {
+      const int r = r0 + tid;
+      const int ho = r / a.Wo, wo = r - ho * a.Wo;
+      int hq, wq;
+      if (MODE == 0) {
+        hq = ho - a.pad; wq = wo - a.pad;
+        for (int t = 0; t < a.KH; ++t) mask |= (uint32_t)(hq + t >= 0 && hq + t < a.Hg) << t;
+        for (int t = 0; t < a.KW; ++t) mask |= (uint32_t)(wq + t >= 0 && wq + t < a.Wg) << (8 + t);
+      } else {
+        hq = ho + a.pad; wq = wo + a.pad;
+        for (int t = 0; t < a.KH; ++t) mask |= (uint32_t)(hq - t >= 0 && hq - t < a.Hg) << t;
+        for (int t = 0; t < a.KW; ++t) mask |= (uint32_t)(wq - t >= 0 && wq - t < a.Wg) << (8 + t);
+      }
+      lin = (img * a.Hg + hq) * a.Wg + wq;
+      mask |= 1u << 31;                                   // row exists (even if every tap is padding)
+    }
+    int lo = valid ? lin : 0x7fffffff, hi = valid ? lin : (int)0x80000000;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(pinfo + 4u * (uint32_t)warp), "r"(lo) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(pinfo + 16u + 4u * (uint32_t)warp), "r"(hi) : "memory");
+    }
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_lin + 4u * tid), "r"(lin) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tab_mask + 4u * tid), "r"(mask) : "memory");
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(wland_bar(s), 1);
+      mbar_init(wready_bar(s), T3_WSPLITW);
+      mbar_init(wfree_bar(s), 1);
+    }
+    for (int t = 0; t < C::TST; ++t) {
+      mbar_init(tfull_bar(t), T3_ASPLITW / 2);
+      mbar_init(tfree_bar(t), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(pfull_bar(b), 1);
+      mbar_init(pfree_bar(b), taps == 1 ? T3_ASPLITW / 2 : T3_ASPLITW);   // 1x1: a chunk belongs to one group
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+  }
+  if (warp == T3_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  int lin_min = 0x7fffffff, lin_max = (int)0x80000000;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int v, w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pinfo + 4u * i));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(pinfo + 16u + 4u * i));
+    lin_min = min(lin_min, v);
+    lin_max = max(lin_max, w);
+  }
+  // the patch: pixels [pstart, pstart + prows) of the gathered tensor
+  const int pstart = MODE == 0 ? lin_min : lin_min - span;
+  const int prows = lin_max - lin_min + span + 1;
+
+  if (warp < T3_WSPLITW) {
+    // ======================= weight splitters: W_lo = W - tf32(W) in shared memory =======================
+    constexpr int NV = C::B_TILE / 16 / (T3_WSPLITW * 32);          // float4 per thread per stage (>= 1 for BN >= 16)
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % C::STAGES;
+      mbar_wait(wland_bar(s), (kb / C::STAGES) & 1);
+      if (!(a.flags & 0x800)) {
+#pragma unroll
+        for (int i = 0; i < (NV > 0 ? NV : 1); ++i) {
+          const uint32_t idx = (uint32_t)(tid + T3_WSPLITW * 32 * i);
+          if (idx < (uint32_t)(C::B_TILE / 16)) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(b_raw(s) + idx * 16u));
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(b_lo(s) + idx * 16u), "f"(lo_part(v.x)),
+                         "f"(lo_part(v.y)), "f"(lo_part(v.z)), "f"(lo_part(v.w))
+                         : "memory");
+          }
+        }
+        fence_async_proxy();
+      }
+      __syncwarp();
+      if (elect_one()) mbar_arrive(wready_bar(s));
+    }
+  } else if (warp < T3_MMA_WARP) {
+    // ======================= A splitters, then epilogue =======================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - T3_WSPLITW) >> 2;    // splitter group (k-block parity); column half in the epilogue
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    int lin;
+    uint32_t vm;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lin) : "r"(tab_lin + 4u * (uint32_t)row));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vm) : "r"(tab_mask + 4u * (uint32_t)row));
+    // patch row of this tile row's tap (0,0); rows past the image stay inside the buffer and are masked to zero
+    const int pr0 = (vm >> 31) ? lin - pstart : (MODE == 0 ? 0 : span);
+    int chunk_seen = -1;
+    for (int kb = half; kb < nk; kb += 2) {
+      const int c = kb / taps, tap = kb - c * taps;
+      const int kh = tap / a.KW, kw = tap - kh * a.KW;
+      const int t = kb % C::TST, pb = c & 1;
+      if (c != chunk_seen) {
+        mbar_wait(pfull_bar(pb), (c >> 1) & 1);
+        chunk_seen = c;
+      }
+      const int sh = kh * a.Wg + kw;
+      const uint32_t pr = (uint32_t)(MODE == 0 ? pr0 + sh : pr0 - sh);
+      const bool ok = ((vm >> kh) & (vm >> (8 + kw)) & 1u) != 0;
+      uint32_t hi[32], lo[32];
+      const uint32_t ar = patch(pb) + pr * 128u;
+      const uint32_t sw = pr & 7u;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(hi[4 * jj]), "=r"(hi[4 * jj + 1]), "=r"(hi[4 * jj + 2]), "=r"(hi[4 * jj + 3])
+                     : "r"(ar + (((uint32_t)jj ^ sw) << 4)));
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        hi[e] = ok ? hi[e] : 0u;
+        lo[e] = __float_as_uint(lo_part(__uint_as_float(hi[e])));
+      }
+      __syncwarp();
+      // last k-block of this chunk for this warp: its reads of the patch are complete
+      if (kb + 2 >= (c + 1) * taps && elect_one()) mbar_arrive(pfree_bar(pb));
+      if (kb >= C::TST) {
+        mbar_wait(tfree_bar(t), ((kb / C::TST) - 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t tcol = tlane + (uint32_t)(t * 64);
+      tmem_st16(tcol, *reinterpret_cast<const uint32_t(*)[16]>(&hi[0]));
+      tmem_st16(tcol + 16u, *reinterpret_cast<const uint32_t(*)[16]>(&hi[16]));
+      if (!(a.flags & 0x800)) {
+        tmem_st16(tcol + 32u, *reinterpret_cast<const uint32_t(*)[16]>(&lo[0]));
+        tmem_st16(tcol + 48u, *reinterpret_cast<const uint32_t(*)[16]>(&lo[16]));
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(tfull_bar(t));
+    }
+    // ---- epilogue: warp (q, half) owns rows 32q..32q+31 and the 16-column chunks half, half+2, ... ----
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const long m = m0 + row;
+    const bool row_ok = row < rows_valid;
+    const uint32_t trow = tlane + (uint32_t)C::ACC0;
+    const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
+#pragma unroll 1
+    for (int c = half * 16; c < BN; c += 32) {
+      float acc[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+      const bool single = (a.flags & 0x800) != 0;
+      const int nacc = single ? nmain : (C::PAIR ? 2 * nmain + 1 : nmain + 1);
+      for (int g = 0; g < nacc; g += 4) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = g + u;
+          if (i < nacc) {
+            const int col = single ? (C::PAIR ? BN + 2 * i * BN : (1 + i) * BN)
+                                   : (i == nacc - 1 ? 0 : (C::PAIR ? BN + i * BN : (1 + i) * BN));
+            tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);
+          }
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (g + u < nacc) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(v[u][e]);
+          }
+        }
+      }
+      if (a.stats) {
+        float s1[16], s2[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { s1[e] = acc[e]; s2[e] = acc[e] * acc[e]; }
+#pragma unroll
+        for (int width = 8, off = 16; width >= 1; width >>= 1, off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < width; ++i) {
+            const float send1 = up ? s1[i] : s1[i + width], send2 = up ? s2[i] : s2[i + width];
+            const float keep1 = up ? s1[i + width] : s1[i], keep2 = up ? s2[i + width] : s2[i];
+            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+          }
+        }
+        s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+        if (!(lane & 1)) {
+          const int ch = c + ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)ch), "f"(s1[0]) : "memory");
+          asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(BN + ch)), "f"(s2[0]) : "memory");
+        }
+      }
+      if (BN >= 32) {
+        // staged in shared memory (both patch buffers are consumed by now) and written by TMA: see conv_tc2.cu
+        float o[16];
+        bias_act16(acc, a.bias ? a.bias + n0 + c : nullptr, a.act, o);
+        stage_out16(base, row, c, o);
+      } else if (row_ok && n0 + c < a.N) {
+        float o[16];
+        bias_act16(acc, a.bias ? a.bias + n0 + c : nullptr, a.act, o);
+        float4* dst = reinterpret_cast<float4*>(a.y + m * a.N + n0 + c);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+      }
+    }
+    if (BN >= 32) {
+      fence_async_proxy();
+      asm volatile("bar.sync 2, %0;" ::"n"(T3_ASPLITW * 32) : "memory");
+      if (warp == T3_WSPLITW && elect_one()) {
+        // y viewed as [image][pixel][channel]: rows past the end of the image are clipped by the TMA unit
+#pragma unroll
+        for (int blk = 0; blk < BN / 32; ++blk)
+          tma_store_3d(&tm_y, base + (uint32_t)blk * (128u * 128u), n0 + 32 * blk, r0, img);
+        tma_store_commit_wait();
+      }
+    }
+    if (a.stats) {
+      asm volatile("bar.sync 1, %0;" ::"n"(T3_ASPLITW * 32) : "memory");
+      const int i = tid - T3_WSPLITW * 32;
+      if (i < 2 * BN) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cta_sums + 4u * (uint32_t)i));
+        const int stat = i / BN, ch = n0 + (i - stat * BN);
+        if (ch < a.N) atomicAdd(a.stats + (long)stat * a.N + ch, (double)v);
+      }
+    }
+  } else if (warp == T3_WTMA_WARP) {
+    // ======================= W tiles by TMA =======================
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % C::STAGES;
+      if (kb >= C::STAGES) mbar_wait(wfree_bar(s), ((kb / C::STAGES) - 1) & 1);
+      if (elect_one()) {
+        const int c = kb / taps, tap = kb - c * taps;
+        mbar_expect_tx(wland_bar(s), C::B_TILE);
+        tma_load_2d(b_raw(s), &tm_w, tap * a.Cg + c * BK, n0, wland_bar(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == T3_PTMA_WARP) {
+    // ======================= patches by TMA: chunk c -> buffer c & 1 =======================
+    const int nbox = (prows + PBOX - 1) / PBOX;
+    for (int c = 0; c < nchunk; ++c) {
+      const int pb = c & 1;
+      if (c >= 2) mbar_wait(pfree_bar(pb), ((c >> 1) - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(pfull_bar(pb), (uint32_t)nbox * PBOX * 128u);
+        for (int i = 0; i < nbox; ++i)
+          tma_load_2d(patch(pb) + (uint32_t)i * PBOX * 128u, &tm_x, c * BK, pstart + i * PBOX, pfull_bar(pb));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);                    // N = 2*BN: [W ; W_lo]
+    const uint32_t d_corr = tmem_base + (uint32_t)C::ACC0;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % C::STAGES, t = kb % C::TST;
+      mbar_wait(wready_bar(s), (kb / C::STAGES) & 1);
+      mbar_wait(tfull_bar(t), (kb / C::TST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
+        const uint32_t ta = tmem_base + (uint32_t)(t * 64), tal = ta + 32u;
+        if (a.flags & 0x800) {
+          const uint32_t d_main = d_corr + (uint32_t)(C::PAIR ? BN + (kb % C::NMAIN) * 2 * BN : (1 + kb % C::NMAIN) * BN);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)
+            umma_tf32_ts(d_main, ta + 8u * k, db + (uint64_t)(k * 32 >> 4), idesc, (kb >= C::NMAIN) || (k != 0));
+        } else if (C::PAIR) {
+          const uint32_t d_pair = d_corr + (uint32_t)(BN + (kb % C::NMAIN) * 2 * BN);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+            umma_tf32_ts(d_pair, ta + 8u * k, db + adv, idesc2, (kb >= C::NMAIN) || (k != 0));
+          }
+        } else {
+          const uint32_t d_main = d_corr + (uint32_t)((1 + kb % C::NMAIN) * BN);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+            umma_tf32_ts(d_corr, ta + 8u * k, dbl + adv, idesc, 1);
+            umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
+          }
+        }
+        umma_commit(wfree_bar(s));
+        umma_commit(tfree_bar(t));
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(acc_bar);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == T3_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+template <int BN, int MODE>
+int launch_tc3(const TcArgs& a, cudaStream_t st) {
+  using C = Cfg3<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM);
+    if (e != cudaSuccess) {
+      fd::set_error("conv_tc3: cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  CUtensorMap tw, tx;
+  int rc = make_map_2d(&tw, a.w, a.N, a.K, BN);
+  if (rc) return rc;
+  rc = make_map_2d(&tx, a.x, (long)a.B * a.Hg * a.Wg, a.Cg, PBOX);
+  if (rc) return rc;
+  CUtensorMap ty = tw;
+  if (BN >= 32) {
+    rc = make_map_3d(&ty, a.y, a.B, (long)a.Ho * a.Wo, a.N, BM);
+    if (rc) return rc;
+  }
+  dim3 grid(a.B * fd::cdiv((long)a.Ho * a.Wo, BM), fd::cdiv(a.N, BN));
+  conv_tc3_kernel<BN, MODE><<<grid, T3_NTHREADS, C::SMEM, st>>>(a, tw, tx, ty);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN>
+bool patch_fits(const TcArgs& a) {
+  // worst-case number of patch rows a 128-pixel tile (inside one image) needs: its own raster span in the
+  // gathered tensor (every output-row change drifts by |Wg - Wo| pixels) + the tap span, in whole TMA boxes
+  const long dW = a.Wg > a.Wo ? a.Wg - a.Wo : a.Wo - a.Wg;
+  const long row_changes = (BM - 2) / a.Wo + 1;
+  const long need = (BM - 1) + dW * row_changes + (long)(a.KH - 1) * a.Wg + a.KW;
+  return (need + PBOX - 1) / PBOX * PBOX <= Cfg3<BN>::PROWS;
+}
+
+}  // namespace
+
+namespace fd {
+// returns -1 when this variant does not take the problem (the caller falls back to conv_tc2)
+int conv_tc3_dispatch(const TcArgs& a, int mode, cudaStream_t st) {
+  if (a.stride != 1 || a.Cg % BK != 0 || a.KH > 8 || a.KW > 8 || a.M >= (1L << 31)) return -1;
+  if ((long)a.B * a.Hg * a.Wg >= (1L << 31) - 65536) return -1;
+  if ((((uintptr_t)a.w | (uintptr_t)a.x | (uintptr_t)a.y) & 15) != 0) return -1;
+  const int bn = a.N % 128 == 0 ? 128 : (a.N % 64 == 0 ? 64 : (a.N % 32 == 0 ? 32 : 16));
+  if (bn == 128) {
+    if (!patch_fits<128>(a)) return -1;
+    return mode == 0 ? launch_tc3<128, 0>(a, st) : launch_tc3<128, 1>(a, st);
+  }
+  if (bn == 64) {
+    if (!patch_fits<64>(a)) return -1;
+    return mode == 0 ? launch_tc3<64, 0>(a, st) : launch_tc3<64, 1>(a, st);
+  }
+  if (bn == 32) {
+    if (!patch_fits<32>(a)) return -1;
+    return mode == 0 ? launch_tc3<32, 0>(a, st) : launch_tc3<32, 1>(a, st);
+  }
+  if (!patch_fits<16>(a)) return -1;
+  return mode == 0 ? launch_tc3<16, 0>(a, st) : launch_tc3<16, 1>(a, st);
+}
+}  // namespace fd

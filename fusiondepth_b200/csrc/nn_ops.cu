@@ -141,6 +141,44 @@ __device__ __forceinline__ void stv(float* p, const float (&v)[VEC]) {
 }
 
 struct BnGeom { int groups, gx, gy; dim3 grid, block; };
+constexpr int BN_MAX_PARTS = 96;      // partial rows of the statistic kernels (workspace: (1 + parts) * 2C doubles + counters)
+
+// Last-block fold of the per-block partial sums: block (bx, by) has written its 2*VEC*nx partials to
+// part[by][...]; the last block of column bx to arrive (ticket) adds the rows in a fixed order, so the result
+// is deterministic and no two blocks ever touch the same address atomically.
+template <int VEC>
+__device__ __forceinline__ void bn_fold_partials(double* __restrict__ ws, double a[VEC], double b[VEC], int c, int C,
+                                                 bool owner) {
+  double* part = ws + 2 * (long)C;
+  unsigned* counter = reinterpret_cast<unsigned*>(part + (long)BN_MAX_PARTS * 2 * C);
+  __shared__ unsigned s_last;
+  if (owner) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      part[(long)blockIdx.y * 2 * C + c + i] = a[i];
+      part[(long)blockIdx.y * 2 * C + C + c + i] = b[i];
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_last = atomicAdd(&counter[blockIdx.x], 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (owner) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      double sa = 0, sb = 0;
+      for (unsigned r = 0; r < gridDim.y; ++r) {
+        sa += part[(long)r * 2 * C + c + i];
+        sb += part[(long)r * 2 * C + C + c + i];
+      }
+      ws[c + i] = sa;
+      ws[C + c + i] = sb;
+    }
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) counter[blockIdx.x] = 0;      // ready for the next use of this workspace
+}
 // reduce = true: geometry of the two statistic kernels.  Their blocks end with 2*C fp64 atomics on the
 // same C addresses, which serialise in L2: a few dozen blocks stream the (L2-sized) tensor just as
 // fast and keep the contention per address small.
@@ -151,8 +189,10 @@ inline BnGeom bn_geom(long M, int C, int vec, bool reduce = false) {
   g.gy = 256 / g.gx;                              // pixel lanes per block
   int bx = (g.groups + g.gx - 1) / g.gx;
   long by = (M + (long)g.gy * 8 - 1) / ((long)g.gy * 8);
-  long cap = reduce ? (48 + bx - 1) / bx : (148L * 8 + bx - 1) / bx;
-  if (reduce && cap < 8) cap = 8;
+  // statistic kernels: every block leaves one partial row (2*C doubles) for the last block of its channel
+  // column to fold, so a few blocks per SM stream the tensor at L2 speed without contended atomics
+  long cap = reduce ? (148L * 2 + bx - 1) / bx : (148L * 8 + bx - 1) / bx;
+  if (reduce && cap > BN_MAX_PARTS) cap = BN_MAX_PARTS;
   if (by > cap) by = cap;
   if (by < 1) by = 1;
   g.grid = dim3(bx, (unsigned)by);
@@ -196,7 +236,9 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict_
     red[((1 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = ss[i];
   }
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
+  double fa[VEC], fb[VEC];
+  const bool owner = threadIdx.y == 0 && c < C;
+  if (owner) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       double a = 0, b = 0;
@@ -204,10 +246,10 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict_
         a += red[((0 * VEC + i) * ny + r) * nx + threadIdx.x];
         b += red[((1 * VEC + i) * ny + r) * nx + threadIdx.x];
       }
-      atomicAdd(&ws[c + i], a);
-      atomicAdd(&ws[C + c + i], b);
+      fa[i] = a; fb[i] = b;
     }
   }
+  bn_fold_partials<VEC>(ws, fa, fb, c, C, owner);
 }
 
 // Per-channel batch statistics from the fp64 sums (training) or the running buffers (eval); the
@@ -325,7 +367,9 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
     red[((1 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = ss[i];
   }
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
+  double fa[VEC], fb[VEC];
+  const bool owner = threadIdx.y == 0 && c < C;
+  if (owner) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       double a = 0, b = 0;
@@ -333,10 +377,10 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
         a += red[((0 * VEC + i) * ny + r) * nx + threadIdx.x];
         b += red[((1 * VEC + i) * ny + r) * nx + threadIdx.x];
       }
-      atomicAdd(&ws[c + i], a);
-      atomicAdd(&ws[C + c + i], b);
+      fa[i] = a; fb[i] = b;
     }
   }
+  bn_fold_partials<VEC>(ws, fa, fb, c, C, owner);
 }
 
 template <int VEC>
@@ -804,6 +848,10 @@ int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long 
   return 0;
 }
 
+size_t fd_bn_workspace_bytes(int C) {
+  return sizeof(double) * (size_t)(1 + BN_MAX_PARTS) * 2 * C + sizeof(unsigned) * (size_t)(C + 32);
+}
+
 int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
               float* running_mean, float* running_var, int training, float momentum, float eps,
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,
@@ -821,7 +869,7 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
   const size_t sm = sizeof(double) * 2 * vec * 256;
   if (training && !stats_ready) {       // stats_ready: ws already holds the sums (fd_conv2d_fwd_tc_stats)
     BnGeom gr = bn_geom(M, C, vec, true);
-    cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
+    cudaMemsetAsync(ws + (size_t)(1 + BN_MAX_PARTS) * 2 * C, 0, sizeof(unsigned) * gr.grid.x, st);
     if (vec == 4) bn_stats_kernel<4><<<gr.grid, gr.block, sm, st>>>(x, ws, M, C);
     else bn_stats_kernel<1><<<gr.grid, gr.block, sm, st>>>(x, ws, M, C);
     FD_CHECK_LAUNCH();
@@ -852,8 +900,8 @@ int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
   const int vec = (C % 4 == 0) ? 4 : 1;
   BnGeom g = bn_geom(M, C, vec);
   const size_t sm = sizeof(double) * 2 * vec * 256;
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st);
   BnGeom gr = bn_geom(M, C, vec, true);
+  cudaMemsetAsync(ws + (size_t)(1 + BN_MAX_PARTS) * 2 * C, 0, sizeof(unsigned) * gr.grid.x, st);
   if (vec == 4) {
     bn_bwd_reduce_kernel<4><<<gr.grid, gr.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
     FD_CHECK_LAUNCH();

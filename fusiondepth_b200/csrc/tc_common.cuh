@@ -22,6 +22,9 @@ struct TcArgs {
 };
 // conv_tc2.cu: A-operand-in-TMEM kernels (mode 0 forward, 1 data gradient)
 int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st);
+// conv_tc3.cu: the same with the input patch fetched once per 32-channel chunk by TMA and W_lo computed in
+// shared memory (stride-1 layers whose patch fits); returns -1 when it does not take the problem
+int conv_tc3_dispatch(const TcArgs& a, int mode, cudaStream_t st);
 }  // namespace fd
 
 namespace {
@@ -101,6 +104,30 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 }
 
 
+// o[e] = act(acc[e] + bias[e]) for one 16-column chunk.  The activation switch sits OUTSIDE the element loop:
+// per element (act_fn in an unrolled loop) ptxas emits sixteen jump tables over ~60 KB of inlined expm1f / expf /
+// tanhf code, and the epilogue spent ~9 k cycles per CTA in indirect branches and instruction-cache misses
+// (23 % of the layer-1 kernel, found with the role trace + SASS).
+__device__ __forceinline__ void bias_act16(const float (&acc)[16], const float* __restrict__ bias, int act,
+                                           float (&o)[16]) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) o[e] = acc[e] + (bias ? bias[e] : 0.f);
+  if (act == FD_ACT_NONE) return;
+  if (act == FD_ACT_RELU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] = fmaxf(o[e], 0.f);
+  } else if (act == FD_ACT_ELU) {
+#pragma unroll 4
+    for (int e = 0; e < 16; ++e) o[e] = o[e] > 0.f ? o[e] : expm1f(o[e]);
+  } else if (act == FD_ACT_SIGMOID) {
+#pragma unroll 4
+    for (int e = 0; e < 16; ++e) o[e] = 1.f / (1.f + expf(-o[e]));
+  } else {
+#pragma unroll 4
+    for (int e = 0; e < 16; ++e) o[e] = tanhf(o[e]);
+  }
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -113,6 +140,34 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// TMA tensor store of a staged [rows x 32 floats] SWIZZLE_128B block (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// One output row chunk (16 floats at tile column c) of tile row `row` into the staged output tile: 32-column
+// blocks of [128 rows x 128 B], 16-byte chunks XOR-swizzled by (row & 7) -- the SWIZZLE_128B image a TMA store
+// expects, and bank-conflict free for "one row per lane" writes.
+__device__ __forceinline__ void stage_out16(uint32_t out_smem, int row, int c, const float (&o)[16]) {
+  const uint32_t blk = out_smem + (uint32_t)(c >> 5) * (128u * 128u) + (uint32_t)row * 128u;
+  const uint32_t j0 = (uint32_t)(c & 31) >> 2, sw = (uint32_t)row & 7u;
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (((j0 + e) ^ sw) << 4)), "f"(o[4 * e]),
+                 "f"(o[4 * e + 1]), "f"(o[4 * e + 2]), "f"(o[4 * e + 3])
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&o)[16]) {
   uint32_t v[16];
   asm volatile(
@@ -208,6 +263,21 @@ int make_map_2d(CUtensorMap* map, const float* ptr, long rows, long cols, int bo
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FD_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld", (int)r,
              rows, cols);
+  return 0;
+}
+
+// 3-D fp32 tensor [d2][d1][cols] (cols contiguous), box = 32 cols x box_rows x 1, SWIZZLE_128B
+int make_map_3d(CUtensorMap* map, const float* ptr, long d2, long d1, long cols, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  FD_REQUIRE(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)cols * sizeof(float), (cuuint64_t)cols * d1 * sizeof(float)};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FD_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(3d) failed (%d) %ldx%ldx%ld", (int)r, d2, d1, cols);
   return 0;
 }
 

@@ -349,7 +349,7 @@ class PadConvParamsFn(torch.autograd.Function):
             _lib.check(lib.fd_pad_rows(_p(dwp), _p(ctx.wg), Cout * KH * KW, cin_p, Cin, 1, st), "fd_pad_rows")
             dw = None
         else:
-            dw = torch.zeros((Cout, Cin, KH, KW), device=dwp.device, dtype=torch.float32, memory_format=CL)
+            dw = torch.empty((Cout, Cin, KH, KW), device=dwp.device, dtype=torch.float32, memory_format=CL).zero_()
             _lib.check(lib.fd_pad_rows(_p(dwp), _p(dw), Cout * KH * KW, cin_p, Cin, 1, st), "fd_pad_rows")
         db = None
         if has_bias and dbp is not None:
@@ -486,7 +486,8 @@ class BatchNormFn(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(C, device=x.device, dtype=torch.float32)
         rstd = torch.empty(C, device=x.device, dtype=torch.float32)
-        ws = stats if stats is not None else torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        ws = stats if stats is not None else torch.empty(lib.fd_bn_workspace_bytes(C) // 8, device=x.device,
+                                                         dtype=torch.float64)
         _lib.check(lib.fd_bn_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(running_mean),
                                  _p(running_var), int(training), momentum, eps, int(relu), _p(y),
                                  _p(mean), _p(rstd), _p(ws), M, C, stat_weight, int(stats is not None),
@@ -509,7 +510,7 @@ class BatchNormFn(torch.autograd.Function):
         direct = ctx.gg is not None and ctx.gb is not None
         dgamma = ctx.gg if direct else torch.empty(C, device=x.device, dtype=torch.float32)
         dbeta = ctx.gb if direct else torch.empty(C, device=x.device, dtype=torch.float32)
-        ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        ws = torch.empty(lib.fd_bn_workspace_bytes(C) // 8, device=x.device, dtype=torch.float64)
         _lib.check(lib.fd_bn_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(mean), _p(rstd), relu, training,
                                  _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, int(direct),
                                  _stream()), "fd_bn_bwd")

@@ -246,13 +246,16 @@ int fd_act_bwd(const float* y, const float* dy, float* dpre, float* dbias, long 
 
 /* BatchNorm2d (+ optional residual add, + optional ReLU) over M = B*H*W rows of C channels.
  * training: batch statistics, running stats updated (momentum, unbiased var).
- * ws: 2*C doubles of scratch.  save_mean/save_rstd [C] are outputs used by the backward.
+ * ws: fd_bn_workspace_bytes(C) bytes of scratch (the first 2*C doubles end up holding the per-channel sums;
+ * the rest are per-block partial rows folded by the last block to finish -- deterministic, no contended
+ * atomics).  save_mean/save_rstd [C] are outputs used by the backward.
  * stat_weight < 0: running = (1-momentum)*running + momentum*stat (nn.BatchNorm2d).  stat_weight >= 0:
  * running += stat_weight*stat with atomics -- for calls of one layer that run concurrently inside an
  * optimiser step, after the caller has decayed the buffers by (1-momentum)^n_calls once.
  * stats_ready != 0: ws already holds the per-channel sum / sum of squares of x (written by
  * fd_conv2d_fwd_tc_stats into a zeroed buffer); the statistics pass over x is skipped.
  * accumulate_param_grads: dgamma/dbeta are added (atomically) into existing buffers instead of set. */
+size_t fd_bn_workspace_bytes(int C);
 int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
               float* running_mean, float* running_var, int training, float momentum, float eps,
               int relu, float* y, float* save_mean, float* save_rstd, double* ws, long M, int C,

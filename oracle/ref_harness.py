@@ -154,10 +154,13 @@ def make_refiner(ns, models, B, H, W, device="cpu"):
 
 class FixedNoise:
     """Context manager: makes torch.randn return the supplied tensors in call order so the
-    reference's trainer.py:551 draws exactly the noise the oracle is given."""
+    reference's trainer.py:551 draws exactly the noise the oracle is given.  `cpu=True` (a CPU run of the
+    reference on a machine that has a GPU): Tensor.cuda() is the identity inside the context, because
+    compute_losses hard-codes `.cuda()` on that noise (trainer.py:551-552, refiner.py:652-653)."""
 
-    def __init__(self, tensors):
+    def __init__(self, tensors, cpu: bool = False):
         self.tensors = list(tensors)
+        self.cpu = cpu
 
     def __enter__(self):
         self._orig = torch.randn
@@ -167,7 +170,12 @@ class FixedNoise:
             return next(it).clone()
 
         torch.randn = fake
+        if self.cpu:
+            self._cuda = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda t, *a, **k: t
         return self
 
     def __exit__(self, *exc):
         torch.randn = self._orig
+        if self.cpu:
+            torch.Tensor.cuda = self._cuda

@@ -27,6 +27,15 @@ CONV_CASES = [
     (1, 22, 20, 28, 22, 3, 1, 0, True, "elu"),       # refine decoder odd channels
     (2, 256, 4, 6, 12, 1, 1, 0, True, "none"),       # pose head
     (2, 48, 10, 14, 40, 3, 1, 1, True, "tanh"),
+    # conv_tc3 (patch variant): several 32-channel chunks with buffer reuse, tiles ending inside an image,
+    # images smaller than a tile, 1x1 (a chunk per k-block), wide rows, BN = 128 / 64 / 32 / 16 tiles
+    (2, 160, 12, 40, 128, 3, 1, 1, False, "none"),   # 5 chunks (double-buffer wrap), 480 px = 3.75 tiles/image
+    (3, 64, 6, 20, 64, 3, 1, 1, False, "relu"),      # 120-pixel images: one partial tile each
+    (2, 128, 10, 14, 256, 1, 1, 0, False, "none"),   # 1x1 stride 1 (Bottleneck): taps == 1
+    (1, 64, 12, 160, 64, 3, 1, 1, True, "elu"),      # layer-1 width: 450-row patches
+    (2, 96, 14, 42, 32, 3, 1, 0, True, "elu"),       # valid conv on padded input, rows shorter than a tile
+    (2, 32, 26, 82, 16, 3, 1, 0, True, "elu"),       # BN = 16
+    (1, 288, 14, 22, 288, 3, 1, 0, True, "elu"),     # refine decoder, channel-padded 262 -> 288
 ]
 
 
