@@ -450,7 +450,11 @@ def run_ours(args):
         step = refine.RefineStep(models, lr=lr)
     else:
         step = training.TrainStep(models, lr=lr, accumulate=ACCUM)
-    cpu_batches, cpu_noises = synthetic_step_inputs(100 + rank, dev)
+    # Every rank feeds its own copy of the same seeded batch: the content does not affect the timing, and with
+    # random-initialised networks distinct random batches empty the si-loss mask on some rank after the first
+    # Adam step (loss = NaN there -- in the reference too), which the gradient all-reduce
+    # would spread to every replica.
+    cpu_batches, cpu_noises = synthetic_step_inputs(100, dev)
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in cpu_batches]
     pinned_noise = [{k: v.pin_memory() for k, v in n.items()} for n in cpu_noises]
     h2d = sum(v.numel() * v.element_size() for b in pinned for v in b.values()) + \
@@ -556,6 +560,14 @@ def run_ours(args):
             torch.distributed.all_reduce(t_e2e, op=torch.distributed.ReduceOp.MAX)
         ms_e2e = float(t_e2e) / args.steps
     _phase("e2e done")
+    replica_drift = None
+    if world > 1:
+        # every rank applied the same averaged gradients to the same initial weights: the replicas must agree
+        ref = step.flat.data.clone()
+        torch.distributed.broadcast(ref, 0)
+        d = (ref - step.flat.data).abs().max().reshape(1)
+        torch.distributed.all_reduce(d, op=torch.distributed.ReduceOp.MAX)
+        replica_drift = float(d)
 
     # Per-kernel-family device times: ONE instrumented eager step on rank 0, on a single stream (no
     # trunk / micro-batch concurrency, no collective) with CUDA events around every conv and loss
@@ -628,6 +640,10 @@ def run_ours(args):
             "loss_first": first_loss, "loss": float(loss),
             "conv_precision": os.environ.get("FD_CONV_PRECISION", "3xtf32"),
         }
+        if world > 1:
+            result["dp"] = {"allreduce": "bucketed, overlapped with backward" if step.bucketed else "single, after backward",
+                            "buckets_floats": [hi - lo for _, lo, hi in step.buckets],
+                            "max_abs_weight_difference_between_replicas": replica_drift}
         parity_ok = True
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline_leg(sds0, cpu_batches, cpu_noises)

@@ -148,7 +148,7 @@ constexpr int BN_MAX_PARTS = 96;      // partial rows of the statistic kernels (
 // is deterministic and no two blocks ever touch the same address atomically.
 template <int VEC>
 __device__ __forceinline__ void bn_fold_partials(double* __restrict__ ws, double a[VEC], double b[VEC], int c, int C,
-                                                 bool owner) {
+                                                 bool owner, double* red) {
   double* part = ws + 2 * (long)C;
   unsigned* counter = reinterpret_cast<unsigned*>(part + (long)BN_MAX_PARTS * 2 * C);
   __shared__ unsigned s_last;
@@ -165,20 +165,41 @@ __device__ __forceinline__ void bn_fold_partials(double* __restrict__ ws, double
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // the whole last block folds: thread (x, y) takes rows y, y + ny, ... of its channels, then the ny lanes meet
+  const int nx = blockDim.x, ny = blockDim.y;
+  double sa[VEC], sb[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sa[i] = sb[i] = 0.0;
+  if (c < C) {
+    for (unsigned r = threadIdx.y; r < gridDim.y; r += ny) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        sa[i] += part[(long)r * 2 * C + c + i];
+        sb[i] += part[(long)r * 2 * C + C + c + i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    red[((0 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = sa[i];
+    red[((1 * VEC + i) * ny + threadIdx.y) * nx + threadIdx.x] = sb[i];
+  }
+  __syncthreads();
   if (owner) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      double sa = 0, sb = 0;
-      for (unsigned r = 0; r < gridDim.y; ++r) {
-        sa += part[(long)r * 2 * C + c + i];
-        sb += part[(long)r * 2 * C + C + c + i];
+      double ta = 0, tb = 0;
+      for (int r = 0; r < ny; ++r) {                      // fixed order: deterministic
+        ta += red[((0 * VEC + i) * ny + r) * nx + threadIdx.x];
+        tb += red[((1 * VEC + i) * ny + r) * nx + threadIdx.x];
       }
-      ws[c + i] = sa;
-      ws[C + c + i] = sb;
+      ws[c + i] = ta;
+      ws[C + c + i] = tb;
     }
   }
   if (threadIdx.x == 0 && threadIdx.y == 0) counter[blockIdx.x] = 0;      // ready for the next use of this workspace
 }
+
 // reduce = true: geometry of the two statistic kernels.  Their blocks end with 2*C fp64 atomics on the
 // same C addresses, which serialise in L2: a few dozen blocks stream the (L2-sized) tensor just as
 // fast and keep the contention per address small.
@@ -249,7 +270,8 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict_
       fa[i] = a; fb[i] = b;
     }
   }
-  bn_fold_partials<VEC>(ws, fa, fb, c, C, owner);
+  __syncthreads();                                         // `red` is reused by the fold
+  bn_fold_partials<VEC>(ws, fa, fb, c, C, owner, red);
 }
 
 // Per-channel batch statistics from the fp64 sums (training) or the running buffers (eval); the
@@ -380,7 +402,8 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
       fa[i] = a; fb[i] = b;
     }
   }
-  bn_fold_partials<VEC>(ws, fa, fb, c, C, owner);
+  __syncthreads();                                         // `red` is reused by the fold
+  bn_fold_partials<VEC>(ws, fa, fb, c, C, owner, red);
 }
 
 template <int VEC>

@@ -103,6 +103,36 @@ class BNSchedule:
 BN_SCHEDULE: Optional[BNSchedule] = None
 
 
+# Weight-gradient kernels off the critical path.  Set by training.TrainStep to a dict {stream -> side stream}:
+# Conv2dFn.backward then launches the weight-gradient kernel on the side stream of the stream it runs on (forked
+# by an event once dy is final), so the data-gradient chain of the backward pass -- the critical path of the
+# step -- no longer waits for it; nothing consumes dW before the gradient exchange.  Only with DIRECT_GRAD (the
+# kernel accumulates into the flat gradient buffer, autograd never sees dW).  WGRAD_KEEP holds x / dy until the
+# step joins the side streams, so the caching allocator cannot hand their memory to the main stream early.
+WGRAD_STREAMS: Optional[Dict] = None
+WGRAD_USED: set = set()
+WGRAD_KEEP: list = []
+
+
+def wgrad_side_stream():
+    if WGRAD_STREAMS is None:
+        return None
+    cur = torch.cuda.current_stream()
+    side = WGRAD_STREAMS.get(cur)
+    if side is None:
+        side = WGRAD_STREAMS[cur] = torch.cuda.Stream(device=cur.device)
+    return side
+
+
+def join_wgrad_streams():
+    """The current stream waits for every weight-gradient side stream used since the last join."""
+    cur = torch.cuda.current_stream()
+    for s in WGRAD_USED:
+        cur.wait_stream(s)
+    WGRAD_USED.clear()
+    WGRAD_KEEP.clear()
+
+
 # Set by training.TrainStep when the gradient exchange is bucketed: callable(bucket_id), invoked from the
 # backward pass of every trunk once the gradients of that bucket have been launched (grad_ready()).
 GRAD_READY = None
@@ -182,9 +212,9 @@ def prep_input(x):
 
 
 # --------------------------------------------------------------------------------------------
-# Experimental (FD_BN_FUSE_STATS=1, not yet validated on hardware): BatchNorm batch statistics out of the
-# tensor-core convolution epilogue instead of a separate pass over the conv output.
-FUSE_BN_STATS = os.environ.get("FD_BN_FUSE_STATS", "0") == "1"
+# BatchNorm batch statistics out of the tensor-core convolution's epilogue instead of a separate pass over the
+# conv output (FD_BN_FUSE_STATS=0 restores the separate bn_stats kernel; both are parity-tested).
+FUSE_BN_STATS = os.environ.get("FD_BN_FUSE_STATS", "1") == "1"
 
 
 def conv_emits_stats(Cin, Cout, has_bias) -> bool:
@@ -304,13 +334,22 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = ctx.wg if ctx.wg is not None else torch.empty(
                 (Cout, Cin, KH, KW), device=x.device, dtype=torch.float32, memory_format=CL).zero_()
+            side = wgrad_side_stream() if (ctx.wg is not None and PROFILE is None) else None
+            wst = st
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())       # dy is final; (the data gradient above only reads it)
+                side.wait_event(ev)
+                WGRAD_USED.add(side)
+                WGRAD_KEEP.append((x, dy))
+                wst = c_void_p(side.cuda_stream)
             with _timed("conv", 2.0 * M * Cout * KH * KW * Cin):
                 if CONV_BACKEND == "tc" and Cin % 32 == 0 and Cout % 32 == 0:
                     _lib.check(lib.fd_conv2d_wgrad_tc(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
-                                                      stride, pad, st), "fd_conv2d_wgrad_tc")
+                                                      stride, pad, wst), "fd_conv2d_wgrad_tc")
                 else:
                     _lib.check(lib.fd_conv2d_wgrad(_p(x), _p(dy), _p(dw), B, H, W, Cin, Cout, KH, KW,
-                                                   stride, pad, st), "fd_conv2d_wgrad")
+                                                   stride, pad, wst), "fd_conv2d_wgrad")
         # gradients written straight into the parameters' buffers are not handed back to autograd
         return (dx, None if ctx.wg is not None else dw, None if ctx.bg is not None else dbias,
                 None, None, None, None)

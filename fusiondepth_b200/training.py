@@ -387,6 +387,10 @@ class TrainStep:
             and os.environ.get("FD_BUCKETED_ALLREDUCE", "1") != "0"
         self.comm_stream = torch.cuda.Stream(device=dev) if self.bucketed else None
         self._ready = None
+        # Opt-in experiment (FD_WGRAD_STREAM=1): weight-gradient kernels on side streams, off the backward pass's
+        # dependency chain (ops.WGRAD_STREAMS).  Measured SLOWER on B200 (359 vs 385 images/s): the step is bound by
+        # SM time, not by dependencies, and the extra concurrency only makes the tensor-core kernels share SMs.
+        self.wgrad_streams = {} if (direct_grad and os.environ.get("FD_WGRAD_STREAM", "0") == "1") else None
         self.direct_grad, self.cache_weight_prep = direct_grad, cache_weight_prep
         # The micro-batches of a step are independent given the weights (gradients accumulate with
         # atomics, BatchNorm running statistics through ops.BNSchedule), so each gets its own stream
@@ -420,9 +424,15 @@ class TrainStep:
 
     def _grad_ready(self, bucket: int):
         """Backward hook (ops.GRAD_READY): the gradients of `bucket` of this trunk call are on the stream."""
+        cur = torch.cuda.current_stream()
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
+        ev.record(cur)
         self._ready[bucket].append(ev)
+        side = self.wgrad_streams.get(cur) if self.wgrad_streams is not None else None
+        if side is not None and side in ops.WGRAD_USED:
+            ev2 = torch.cuda.Event()
+            ev2.record(side)                              # the bucket's weight-gradient kernels run there
+            self._ready[bucket].append(ev2)
 
     def _make_bn_schedule(self):
         """Calls per optimiser step of every BatchNorm layer: the pose trunks see both image pairs
@@ -442,6 +452,7 @@ class TrainStep:
         ops.DIRECT_GRAD = self.direct_grad
         ops.WEIGHT_CACHE = {} if self.cache_weight_prep else None
         ops.BN_SCHEDULE = self.bn_schedule
+        ops.WGRAD_STREAMS = self.wgrad_streams
         if self.bucketed:
             self._ready = [[] for _ in range(N_BUCKETS)]
             ops.GRAD_READY = self._grad_ready
@@ -459,6 +470,7 @@ class TrainStep:
             ops.WEIGHT_CACHE = None
             ops.BN_SCHEDULE = None
             ops.GRAD_READY = None
+            ops.WGRAD_STREAMS = None
 
     def _micro_batch(self, inputs, noise, trunks):
         _, losses = process_batch(self.models, inputs, noise, self.opts, streams=trunks)
@@ -497,6 +509,7 @@ class TrainStep:
         inside every trunk), so inside the captured graph it runs under the rest of the backward pass;
         only the last bucket (layers 1-2 and the stems) is exposed."""
         nt = self.flat.n_train
+        ops.join_wgrad_streams()
         if self.world > 1:
             end = self.buckets[-1][2] if self.buckets else nt       # the unused fc heads are not exchanged
             if self.bucketed:

@@ -190,7 +190,7 @@ def test_cuda_graph_replay_matches_eager(cuda):
     assert abs(l_graph - l_eager) < 1e-5 * abs(l_eager)
     # the flat gradient buffers themselves (fp32 atomics: summation order varies run to run)
     assert float(g_eager.abs().max()) > 0
-    assert rel_err(g_graph.cpu(), g_eager.cpu()) < 1e-4
+    assert rel_err(g_graph.cpu(), g_eager.cpu()) < 5e-4
     # per parameter, so that small-gradient tensors are checked at their own scale
     for p in step.flat.params[::7]:
         off, k = step.flat.offsets[p], p.numel()
