@@ -348,6 +348,32 @@ def lidar_leg(dev, n_frames=36):
             "in_timed_step": False}
 
 
+def eval_leg(models, dev, iters=50):
+    """Inference path (evaluate_depth.py:173-237 wiring): batch-1 latency of encoder + beam
+    encoder + depth decoder with BatchNorm folded into the convolutions, one CUDA-graph replay per frame, input
+    copied in and disparity produced on the device.  Informative; not part of the timed training step."""
+    from fusiondepth_b200 import evaluation
+    keep = {k: m.training for k, m in models.items()}
+    try:
+        run = evaluation.EvalRunner({k: models[k] for k in ("encoder", "beam_encoder", "depth")}, 1, H, W)
+        x = {("color", 0, 0): torch.rand(1, 3, H, W, device=dev), "2channel": torch.rand(1, 2, H, W, device=dev)}
+        for _ in range(5):
+            run(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            run(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return {"what": "batch-1 inference (encoder + beam encoder + depth decoder, BN folded, CUDA graph), %dx%d" % (W, H),
+                "latency_ms": ms, "frames_per_s": 1e3 / ms}
+    finally:
+        for k, m in models.items():
+            m.train(keep[k])
+
+
 def cpu_baseline_leg(sds0, batches, noises):
     """Bounded CPU sample on rank 0: one optimiser step (ACCUM micro-batches, fwd+bwd) after one warm-up
     micro-batch -- on the SAME initial weights and the SAME batch as the CUDA arm's first step, so its loss is
@@ -572,7 +598,7 @@ def run_ours(args):
     # Per-kernel-family device times: ONE instrumented eager step on rank 0, on a single stream (no
     # trunk / micro-batch concurrency, no collective) with CUDA events around every conv and loss
     # launch, so each event pair brackets one kernel running alone; the whole serial step is timed too.
-    fam, serial_ms, dom, lidar_rf = {}, None, None, None
+    fam, serial_ms, dom, lidar_rf, eval_rf = {}, None, None, None, None
     if rank == 0:
         ops.PROFILE = {}
         step.world = 1
@@ -593,6 +619,10 @@ def run_ours(args):
         step.trunks, step.concurrent = keep
         dom = dominant_kernel_leg(dev)
         lidar_rf = lidar_leg(dev)
+        try:
+            eval_rf = eval_leg(models, dev) if KIND == "trainer" else None
+        except Exception as ex:                     # noqa: BLE001  (informative leg: never lose the bench line)
+            eval_rf = {"unavailable": repr(ex)[:200]}
     _phase("instrumented step done")
 
     result = None
@@ -637,6 +667,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roofline, "roofline_loss": roofline_loss, "roofline_lidar": lidar_rf,
+            "inference": eval_rf,
             "loss_first": first_loss, "loss": float(loss),
             "conv_precision": os.environ.get("FD_CONV_PRECISION", "3xtf32"),
         }

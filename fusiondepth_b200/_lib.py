@@ -74,6 +74,8 @@ _SIGNATURES = {
     "fd_refine_pack": (c_int, [_P, _P, _P, POINTER(c_void_p * 4), _I, _I, _I, _I, _I, _I, _I, _F, _F,
                                POINTER(c_void_p * 4), _P, _P, _P]),
     "fd_masked_median_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "fd_depth_errors_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "fd_depth_errors": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _F, _F, _I, _I, _F, _F, _P, _P, _P]),
     "fd_masked_median": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
     "fd_prep_input": (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
     "fd_stem_im2col": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
@@ -108,6 +110,7 @@ _SIGNATURES = {
     "fd_assemble_fwd": (c_int, [POINTER(Segment), _I, _P, _I, _I, _I, _I, _P]),
     "fd_assemble_bwd": (c_int, [_P, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), _I, _I, _I, _I, _I, _P]),
     "fd_add": (c_int, [_P, _P, _P, _L, _P]),
+    "fd_add_relu": (c_int, [_P, _P, _P, _L, _P]),
     "fd_mean_hw_fwd": (c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "fd_mean_hw_bwd": (c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "fd_adam_step": (c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P, _F, _P]),

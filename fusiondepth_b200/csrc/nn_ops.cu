@@ -760,6 +760,17 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
     o[i] = a[i] + b[i];
 }
 
+__global__ void add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                float* __restrict__ o, long n4) {
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4* o4 = reinterpret_cast<float4*>(o);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 x = a4[i], y = b4[i];
+    o4[i] = make_float4(fmaxf(x.x + y.x, 0.f), fmaxf(x.y + y.y, 0.f), fmaxf(x.z + y.z, 0.f), fmaxf(x.w + y.w, 0.f));
+  }
+}
+
 __global__ void mean_hw_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C,
                                    float scale) {
   const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1010,6 +1021,14 @@ int fd_assemble_bwd(const float* dout, float* const* dsegs, const int* C, const 
 
 int fd_add(const float* a, const float* b, float* out, long n, void* stream) {
   add_kernel<<<min(fd::cdiv(n, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+int fd_add_relu(const float* a, const float* b, float* out, long n, void* stream) {
+  FD_REQUIRE(n % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0,
+             "fd_add_relu: needs 16-byte aligned tensors with a multiple of 4 elements");
+  add_relu_kernel<<<min(fd::cdiv(n / 4, 256), 148 * 16), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4);
   FD_CHECK_LAUNCH();
   return 0;
 }

@@ -76,13 +76,15 @@ __global__ void pool_pyramid_kernel(const float* __restrict__ d0, float* p1, flo
 
 // ---- (2) indices of the masked pixels (mask_src > 0 inside the crop window) ---------------------------
 __global__ void mask_compact_kernel(const float* __restrict__ mask_src, int B, int H, int W, int y0, int y1, int x0,
-                                    int x1, int* __restrict__ count, int* __restrict__ idx) {
+                                    int x1, float mask_lo, float mask_hi, int* __restrict__ count,
+                                    int* __restrict__ idx) {
   const int cw = x1 - x0, ch = y1 - y0;
   const long n = (long)B * ch * cw;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int x = x0 + (int)(i % cw), y = y0 + (int)((i / cw) % ch), b = (int)(i / ((long)cw * ch));
     long o = ((long)b * H + y) * W + x;
-    bool on = mask_src[o] > 0.f;
+    const float mv = mask_src[o];
+    bool on = mv > mask_lo && mv < mask_hi;
     // warp-aggregated append
     unsigned m = __ballot_sync(__activemask(), on);
     if (on) {
@@ -101,7 +103,8 @@ struct MedianArgs {
   const int* count;
   const int* idx;
   int nsrc;
-  // source j: kind 0 = x[idx] * scale ; kind 1 = depth(bilinear(pyr -> HxW)) at idx
+  // source j: kind 0 = x[idx] * scale ; kind 1 = depth(bilinear(pyr -> HxW)) at idx ; kind 2 = 1 / x[idx]
+  int avg_even;        // numpy.median semantics: mean of the two middle elements when the count is even
   const float* src[5];
   int kind[5];
   int h[5], w[5];
@@ -113,6 +116,8 @@ struct MedianArgs {
 
 __device__ __forceinline__ float median_value(const MedianArgs& a, int j, int o) {
   if (a.kind[j] == 0) return __fmul_rn(a.src[j][o], a.scale[j]);
+  if (a.kind[j] == 2) return __fdiv_rn(1.0f, a.src[j][o]);
+  if (a.kind[j] == 3) return fminf(fmaxf(a.src[j][o], a.min_disp), a.range);      // clamp(x, lo, hi)
   const int HW = a.H * a.W;
   int b = o / HW, r = o - b * HW, y = r / a.W, x = r - y * a.W;
   float d = bilerp_up(a.src[j] + (long)b * a.h[j] * a.w[j], y, x, a.h[j], a.w[j], a.H, a.W);
@@ -136,31 +141,38 @@ __global__ void __launch_bounds__(1024) radix_median_kernel(MedianArgs a) {
     if (threadIdx.x == 0) a.out[j] = __int_as_float(0x7fc00000);
     return;
   }
-  if (threadIdx.x == 0) { s_prefix = 0u; s_k = (unsigned)((n - 1) / 2); }
-  unsigned mask = 0u;
-  for (int pass = 3; pass >= 0; --pass) {
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+  float result[2];
+  const int nsel = (a.avg_even && (n & 1) == 0) ? 2 : 1;
+  for (int sel = 0; sel < nsel; ++sel) {
     __syncthreads();
-    const unsigned prefix = s_prefix;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned key = order_key(median_value(a, j, a.idx[i]));
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned k = s_k, cum = 0u;
-      int bkt = 0;
-      for (; bkt < 256; ++bkt) {
-        if (cum + hist[bkt] > k) break;
-        cum += hist[bkt];
+    if (threadIdx.x == 0) { s_prefix = 0u; s_k = (unsigned)(sel == 0 ? (n - 1) / 2 : n / 2); }
+    unsigned mask = 0u;
+    for (int pass = 3; pass >= 0; --pass) {
+      if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+      __syncthreads();
+      const unsigned prefix = s_prefix;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned key = order_key(median_value(a, j, a.idx[i]));
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
       }
-      s_k = k - cum;
-      s_prefix = prefix | ((unsigned)bkt << (8 * pass));
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned k = s_k, cum = 0u;
+        int bkt = 0;
+        for (; bkt < 256; ++bkt) {
+          if (cum + hist[bkt] > k) break;
+          cum += hist[bkt];
+        }
+        s_k = k - cum;
+        s_prefix = prefix | ((unsigned)bkt << (8 * pass));
+      }
+      mask |= 0xffu << (8 * pass);
+      __syncthreads();
     }
-    mask |= 0xffu << (8 * pass);
-    __syncthreads();
+    result[sel] = key_value(s_prefix);
   }
-  if (threadIdx.x == 0) a.out[j] = key_value(s_prefix);
+  if (threadIdx.x == 0)
+    a.out[j] = nsel == 2 ? __fmul_rn(__fadd_rn(result[0], result[1]), 0.5f) : result[0];
 }
 
 // ---- (4) the pack ---------------------------------------------------------------------------------------
@@ -291,13 +303,14 @@ int fd_refine_pack(const float* disp0, const float* beam, const float* two_cha, 
   pool_pyramid_kernel<<<fd::cdiv(hw / 4, 256), 256, 0, st>>>(disp0, v.pyr[1], v.pyr[2], v.pyr[3], B, H, W);
   FD_CHECK_LAUNCH();
   const long nc = (long)B * (crop_y1 - crop_y0) * (crop_x1 - crop_x0);
-  mask_compact_kernel<<<fd::cdiv(nc, 256), 256, 0, st>>>(beam, B, H, W, crop_y0, crop_y1, crop_x0, crop_x1, v.count,
-                                                         v.idx);
+  mask_compact_kernel<<<fd::cdiv(nc, 256), 256, 0, st>>>(beam, B, H, W, crop_y0, crop_y1, crop_x0, crop_x1, 0.f,
+                                                         INFINITY, v.count, v.idx);
   FD_CHECK_LAUNCH();
   const float min_disp = (float)(1.0 / (double)max_depth);
   const float range = (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth);
   MedianArgs m;
   m.count = v.count; m.idx = v.idx; m.nsrc = 5; m.H = H; m.W = W; m.min_disp = min_disp; m.range = range;
+  m.avg_even = 0;
   m.out = v.med;
   m.src[0] = beam; m.kind[0] = 0; m.scale[0] = 100.0f; m.h[0] = H; m.w[0] = W;
   for (int s = 0; s < 4; ++s) {
@@ -333,12 +346,126 @@ int fd_masked_median(const float* x, const float* mask_src, int B, int H, int W,
   cudaError_t e = cudaMemsetAsync(count, 0, 16 * sizeof(int), st);
   FD_REQUIRE(e == cudaSuccess, "fd_masked_median: memset failed: %s", cudaGetErrorString(e));
   const long nc = (long)B * (y1 - y0) * (x1 - x0);
-  mask_compact_kernel<<<fd::cdiv(nc, 256), 256, 0, st>>>(mask_src, B, H, W, y0, y1, x0, x1, count, idx);
+  mask_compact_kernel<<<fd::cdiv(nc, 256), 256, 0, st>>>(mask_src, B, H, W, y0, y1, x0, x1, 0.f, INFINITY, count, idx);
   FD_CHECK_LAUNCH();
   MedianArgs m;
+  m.avg_even = 0;
   m.count = count; m.idx = idx; m.nsrc = 1; m.H = H; m.W = W; m.min_disp = 0.f; m.range = 0.f; m.out = out;
   m.src[0] = x; m.kind[0] = 0; m.scale[0] = scale; m.h[0] = H; m.w[0] = W;
   radix_median_kernel<<<1, 1024, 0, st>>>(m);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- depth error metrics ------------------------------------------------------------------------------
+// layers.compute_depth_errors / evaluate_depth.compute_errors (layers.py:284-302, evaluate_depth.py:42-60) behind
+// the masking, median scaling and clamping of Trainer.compute_depth_losses (trainer.py:598-630) and of the
+// evaluate_depth.py loop (evaluate_depth.py:344-378, 470-478): three launches, nothing leaves the device.
+//   mask  = gt > mask_lo && gt < mask_hi inside rows [y0,y1) x cols [x0,x1)
+//   pred  = pred_is_disp ? 1 / p : clamp(p, pre_min, pre_max)          (the tensor is already at gt's size)
+//   ratio = median(gt[mask]) / median(pred[mask])  (numpy_median: mean of the middle two for even counts;
+//           otherwise torch.median's lower median); pred = clamp(pred * ratio, pred_min, pred_max)
+//   out[0..6] = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3 ; out[7] = number of masked pixels ; out[8] = ratio
+int fd_depth_errors(const float* gt, const float* pred, int B, int H, int W, int y0, int y1, int x0, int x1,
+                    float mask_lo, float mask_hi, int pred_is_disp, float pre_min, float pre_max,
+                    int median_scaling, int numpy_median, float pred_min, float pred_max, float* out,
+                    void* workspace, void* stream);
+
+namespace {
+struct ErrArgs {
+  const float* gt;
+  const float* pred;
+  const int* count;
+  const int* idx;
+  const float* med;       // [2]: median gt, median pred
+  int pred_is_disp, median_scaling;
+  float pre_min, pre_max, pred_min, pred_max;
+  double* acc;            // [8]
+};
+
+__device__ __forceinline__ float err_pred(const ErrArgs& a, int o) {
+  const float p = a.pred[o];
+  return a.pred_is_disp ? __fdiv_rn(1.0f, p) : fminf(fmaxf(p, a.pre_min), a.pre_max);
+}
+
+__global__ void depth_errors_kernel(ErrArgs a) {
+  __shared__ double red[7 * 32];
+  const int n = *a.count;
+  const float ratio = a.median_scaling ? __fdiv_rn(a.med[0], a.med[1]) : 1.0f;
+  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int o = a.idx[i];
+    const float g = a.gt[o];
+    float p = __fmul_rn(err_pred(a, o), ratio);
+    p = fminf(fmaxf(p, a.pred_min), a.pred_max);
+    const float d = __fadd_rn(g, -p);
+    const float th = fmaxf(__fdiv_rn(g, p), __fdiv_rn(p, g));
+    const float dl = __fadd_rn(logf(g), -logf(p));
+    s[0] += (double)__fdiv_rn(fabsf(d), g);
+    s[1] += (double)__fdiv_rn(__fmul_rn(d, d), g);
+    s[2] += (double)__fmul_rn(d, d);
+    s[3] += (double)__fmul_rn(dl, dl);
+    s[4] += th < 1.25f ? 1.0 : 0.0;
+    s[5] += th < 1.5625f ? 1.0 : 0.0;
+    s[6] += th < 1.953125f ? 1.0 : 0.0;
+  }
+  fd::block_sum<7>(s, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 7; ++k) atomicAdd(a.acc + k, s[k]);
+}
+
+__global__ void depth_errors_finalize_kernel(const double* __restrict__ acc, const int* __restrict__ count,
+                                             const float* __restrict__ med, int median_scaling, float* out) {
+  const double n = (double)*count;
+  out[0] = (float)(acc[0] / n);
+  out[1] = (float)(acc[1] / n);
+  out[2] = (float)sqrt(acc[2] / n);
+  out[3] = (float)sqrt(acc[3] / n);
+  out[4] = (float)(acc[4] / n);
+  out[5] = (float)(acc[5] / n);
+  out[6] = (float)(acc[6] / n);
+  out[7] = (float)n;
+  out[8] = median_scaling ? __fdiv_rn(med[0], med[1]) : 1.0f;
+}
+}  // namespace
+
+size_t fd_depth_errors_workspace_bytes(int B, int H, int W) { return (64 + (size_t)B * H * W) * sizeof(float); }
+
+int fd_depth_errors(const float* gt, const float* pred, int B, int H, int W, int y0, int y1, int x0, int x1,
+                    float mask_lo, float mask_hi, int pred_is_disp, float pre_min, float pre_max,
+                    int median_scaling, int numpy_median, float pred_min, float pred_max, float* out,
+                    void* workspace, void* stream) {
+  y0 = y0 < 0 ? 0 : y0; x0 = x0 < 0 ? 0 : x0;
+  y1 = y1 > H ? H : y1; x1 = x1 > W ? W : x1;
+  FD_REQUIRE(B > 0 && y1 > y0 && x1 > x0, "fd_depth_errors: empty window");
+  cudaStream_t st = (cudaStream_t)stream;
+  // workspace: [count (16 ints)] [med (16 floats)] [acc (8 doubles = 16 floats... 32 floats reserved)] [idx]
+  int* count = (int*)workspace;
+  float* med = (float*)workspace + 16;
+  double* acc = (double*)((float*)workspace + 32);
+  int* idx = (int*)workspace + 64;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 64 * sizeof(float), st);
+  FD_REQUIRE(e == cudaSuccess, "fd_depth_errors: memset failed: %s", cudaGetErrorString(e));
+  const long nc = (long)B * (y1 - y0) * (x1 - x0);
+  mask_compact_kernel<<<fd::cdiv(nc, 256), 256, 0, st>>>(gt, B, H, W, y0, y1, x0, x1, mask_lo, mask_hi, count, idx);
+  FD_CHECK_LAUNCH();
+  if (median_scaling) {
+    MedianArgs m;
+    m.count = count; m.idx = idx; m.nsrc = 2; m.H = H; m.W = W; m.min_disp = 0.f; m.range = 0.f; m.out = med;
+    m.avg_even = numpy_median;
+    m.src[0] = gt; m.kind[0] = 0; m.scale[0] = 1.f; m.h[0] = H; m.w[0] = W;
+    m.src[1] = pred; m.kind[1] = pred_is_disp ? 2 : 3; m.scale[1] = 1.f; m.h[1] = H; m.w[1] = W;
+    m.min_disp = pre_min; m.range = pre_max;              // kind 3: clamp(x, min_disp, range)
+    radix_median_kernel<<<2, 1024, 0, st>>>(m);
+    FD_CHECK_LAUNCH();
+  }
+  ErrArgs a;
+  a.gt = gt; a.pred = pred; a.count = count; a.idx = idx; a.med = med; a.pred_is_disp = pred_is_disp;
+  a.median_scaling = median_scaling; a.pre_min = pre_min; a.pre_max = pre_max; a.pred_min = pred_min;
+  a.pred_max = pred_max; a.acc = acc;
+  depth_errors_kernel<<<148, 256, 0, st>>>(a);
+  FD_CHECK_LAUNCH();
+  depth_errors_finalize_kernel<<<1, 1, 0, st>>>(acc, count, med, median_scaling, out);
   FD_CHECK_LAUNCH();
   return 0;
 }

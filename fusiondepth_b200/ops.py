@@ -450,7 +450,7 @@ class StemConvFn(torch.autograd.Function):
     carries no gradient; the weight gradient is a tensor-core GEMM over the saved rows."""
 
     @staticmethod
-    def forward(ctx, x, weight):
+    def forward(ctx, x, weight, bias=None, act=0):
         _require_cuda(x, "stem_conv")
         lib = _lib.load()
         x = x.contiguous()
@@ -476,8 +476,9 @@ class StemConvFn(torch.autograd.Function):
         wpad, wlo = _cached((w.data_ptr(), "stem"), make_pad)
         y = empty_nhwc(B, Cout, Ho, Wo, x.device)
         with _timed("conv", 2.0 * B * Ho * Wo * Cout * K):
-            _lib.check(lib.fd_conv2d_fwd_tc(_p(A), _p(wpad), _p(wlo), None, _p(y), B, Ho, Wo, Kpad, Cout,
-                                            1, 1, 1, 0, 0, st), "fd_conv2d_fwd_tc")
+            _lib.check(lib.fd_conv2d_fwd_tc(_p(A), _p(wpad), _p(wlo), _p(bias), _p(y), B, Ho, Wo, Kpad, Cout,
+                                            1, 1, 1, 0, act, st), "fd_conv2d_fwd_tc")
+        ctx.fused_epilogue = bias is not None or act != 0
         ctx.save_for_backward(A)
         ctx.cfg = (B, Ho, Wo, Kpad, Cout, C, KH, KW, K)
         ctx.wg = _direct_grad(weight)
@@ -486,6 +487,8 @@ class StemConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.load()
+        if ctx.fused_epilogue:
+            raise NotImplementedError("stem_conv: bias / activation are inference-only (folded BatchNorm)")
         (A,) = ctx.saved_tensors
         B, Ho, Wo, Kpad, Cout, C, KH, KW, K = ctx.cfg
         dy = nhwc(dy)
@@ -496,18 +499,19 @@ class StemConvFn(torch.autograd.Function):
                        "fd_conv2d_wgrad_tc")
         if ctx.wg is not None:
             _lib.check(lib.fd_pad_rows(_p(dwpad), _p(ctx.wg), Cout, Kpad, K, 1, st), "fd_pad_rows")
-            return None, None
+            return None, None, None, None
         dw = torch.empty((Cout, C, KH, KW), device=dy.device, dtype=torch.float32, memory_format=CL)
         _lib.check(lib.fd_pad_rows(_p(dwpad), _p(dw), Cout, Kpad, K, 0, st), "fd_pad_rows")
-        return None, dw
+        return None, dw, None, None
 
 
-def stem_conv(x, weight):
-    """(x-0.45)/0.225 -> 7x7/2 conv, NHWC output.  Tensor-core path when enabled."""
+def stem_conv(x, weight, bias=None, act="none"):
+    """(x-0.45)/0.225 -> 7x7/2 conv, NHWC output.  Tensor-core path when enabled.  bias / act: inference only
+    (a BatchNorm folded into the stem)."""
     Cout, C, KH, KW = weight.shape
     if CONV_BACKEND == "tc" and (KH, KW) == (7, 7) and Cout % 32 == 0:
-        return StemConvFn.apply(x, weight)
-    return conv2d(prep_input(x), weight, None, 2, 3, "none")
+        return StemConvFn.apply(x, weight, bias, ACT[act])
+    return conv2d(prep_input(x), weight, bias, 2, 3, act)
 
 
 # --------------------------------------------------------------------------------------------
@@ -689,6 +693,15 @@ class AddFn(torch.autograd.Function):
 
 def add(a, b):
     return AddFn.apply(a, b)
+
+
+def add_relu(a, b):
+    """relu(a + b), inference only (no autograd)."""
+    _require_cuda(a, "add_relu")
+    a, b = nhwc(a), nhwc(b)
+    out = torch.empty_like(a)
+    _lib.check(_lib.load().fd_add_relu(_p(a), _p(b), _p(out), a.numel(), _stream()), "fd_add_relu")
+    return out
 
 
 class MeanHWFn(torch.autograd.Function):
@@ -1052,6 +1065,31 @@ def refine_pack(disp0, beam, two_cha, inv_Ks, crop=(78, 190, 23, 617), min_depth
                                       int(crop[0]), int(crop[1]), int(crop[2]), int(crop[3]), min_depth, max_depth,
                                       ctypes.byref(out_arr), _p(ratios), _p(ws), _stream()), "fd_refine_pack")
     return outs, ratios
+
+
+DEPTH_METRIC_NAMES = ("abs_rel", "sq_rel", "rmse", "rmse_log", "a1", "a2", "a3")
+
+
+def depth_errors(gt, pred, window=None, mask_lo=0.0, mask_hi=float("inf"), pred_is_disp=False,
+                 pre_clamp=(-float("inf"), float("inf")), median_scaling=True, numpy_median=False,
+                 clamp=(1e-3, 80.0)):
+    """The 7 depth metrics (+ count, ratio) of layers.compute_depth_errors behind the reference's masking /
+    median scaling / clamping (fd_depth_errors): a [9] device tensor.  gt and pred have the same size."""
+    _require_cuda(gt, "depth_errors")
+    lib = _lib.load()
+    gt, pred = _nchw(gt.detach()), _nchw(pred.detach())
+    if gt.numel() != pred.numel():
+        raise RuntimeError("depth_errors: gt %s and prediction %s differ in size" % (tuple(gt.shape), tuple(pred.shape)))
+    H, W = gt.shape[-2:]
+    B = gt.numel() // (H * W)
+    y0, y1, x0, x1 = window if window is not None else (0, H, 0, W)
+    out = torch.empty(9, device=gt.device, dtype=torch.float32)
+    ws = torch.empty(lib.fd_depth_errors_workspace_bytes(B, H, W) // 4, device=gt.device, dtype=torch.float32)
+    _lib.check(lib.fd_depth_errors(_p(gt), _p(pred), B, H, W, int(y0), int(y1), int(x0), int(x1), float(mask_lo),
+                                   float(mask_hi), int(pred_is_disp), float(pre_clamp[0]), float(pre_clamp[1]),
+                                   int(median_scaling), int(numpy_median), float(clamp[0]), float(clamp[1]),
+                                   _p(out), _p(ws), _stream()), "fd_depth_errors")
+    return out
 
 
 def masked_median(x, mask_src, window=None, scale=1.0):

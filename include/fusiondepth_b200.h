@@ -152,6 +152,20 @@ int fd_refine_pack(const float* disp0, const float* beam, const float* two_cha, 
                    int B, int H, int W, int crop_y0, int crop_y1, int crop_x0, int crop_x1, float min_depth,
                    float max_depth, float* const out[4], float* ratios, void* workspace, void* stream);
 size_t fd_masked_median_workspace_bytes(int B, int H, int W);
+/* Depth error metrics with the masking, median scaling and clamping of Trainer.compute_depth_losses
+ * (trainer.py:598-630; layers.compute_depth_errors, layers.py:284-302) and of evaluate_depth.py's per-frame
+ * loop (evaluate_depth.py:42-60, 344-378, 470-478), entirely on the device:
+ *   mask  = gt > mask_lo && gt < mask_hi inside rows [y0,y1) x cols [x0,x1);
+ *   p     = pred_is_disp ? 1 / pred : clamp(pred, pre_min, pre_max)      (pred already has gt's size);
+ *   ratio = median(gt[mask]) / median(p[mask]) when median_scaling (numpy_median: numpy.median, i.e. the mean
+ *           of the middle two for even counts; else torch.median's lower median);
+ *   p     = clamp(p * ratio, pred_min, pred_max);
+ *   out[0..6] = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3; out[7] = masked pixel count; out[8] = ratio. */
+size_t fd_depth_errors_workspace_bytes(int B, int H, int W);
+int fd_depth_errors(const float* gt, const float* pred, int B, int H, int W, int y0, int y1, int x0, int x1,
+                    float mask_lo, float mask_hi, int pred_is_disp, float pre_min, float pre_max,
+                    int median_scaling, int numpy_median, float pred_min, float pred_max, float* out,
+                    void* workspace, void* stream);
 int fd_masked_median(const float* x, const float* mask_src, int B, int H, int W, int y0, int y1, int x0,
                      int x1, float scale, float* out, void* workspace, void* stream);
 
@@ -287,6 +301,9 @@ int fd_assemble_bwd(const float* dout, float* const* dsegs_host, const int* C_ho
                     const int* up_host, int nseg, int B, int H, int W, int pad, void* stream);
 
 int fd_add(const float* a, const float* b, float* out, long n, void* stream);
+/* out = relu(a + b): the residual join of a BasicBlock / Bottleneck whose BatchNorms are folded into the
+ * convolutions (inference: fusiondepth_b200.evaluation) */
+int fd_add_relu(const float* a, const float* b, float* out, long n, void* stream);
 /* y[b,c] = scale * mean_hw x[b,:,c]  (pose_decoder.py:44-46) */
 int fd_mean_hw_fwd(const float* x, float* y, int B, int HW, int C, float scale, void* stream);
 int fd_mean_hw_bwd(const float* dy, float* dx, int B, int HW, int C, float scale, void* stream);
