@@ -691,9 +691,21 @@ static bool tc_use_v3() {
   }
   return v == 1;
 }
-// conv_tc3 (patch variant) where it applies, else conv_tc2
+static bool tc_use_v4() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FD_CONV_TC4");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+// conv_tc4 (persistent patch variant) for many-tile launches, conv_tc3 (patch variant) where it applies, else conv_tc2
 static int tc_v2_or_v3(const TcArgs& a, int mode, cudaStream_t st) {
   if (tc_use_v3() && !(a.flags & ~0x800)) {
+    if (tc_use_v4()) {
+      int rc = fd::conv_tc4_dispatch(a, mode, st);
+      if (rc >= 0) return rc;
+    }
     int rc = fd::conv_tc3_dispatch(a, mode, st);
     if (rc >= 0) return rc;
   }
@@ -747,6 +759,7 @@ int fd_conv2d_fwd_tc_stats(const float* x, const float* w, const float* w_lo, co
   FD_REQUIRE(stats == nullptr || (tc_use_v2() && bias == nullptr && act == FD_ACT_NONE),
              "fd_conv2d_fwd_tc_stats: channel statistics need the conv_tc2 kernels, no bias and no activation");
   TcArgs a;
+  a.trace = nullptr;
   a.stats = stats;
   a.x = x; a.w = w; a.wlo = w_lo; a.bias = bias; a.y = y;
   a.B = B; a.Hg = H; a.Wg = W; a.Cg = Cin;
@@ -765,6 +778,7 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
   FD_REQUIRE(fd_conv2d_tc_supported(Cout, Cin),
              "fd_conv2d_dgrad_tc: needs Cout %% 32 == 0 and Cin %% 16 == 0 (got %d, %d)", Cout, Cin);
   TcArgs a;
+  a.trace = nullptr;
   a.stats = nullptr;
   a.x = dy; a.w = wt; a.wlo = wt_lo; a.bias = nullptr; a.y = dx;
   a.B = B;

@@ -24,7 +24,7 @@ namespace {
 
 constexpr int NLOADW2 = 4, NLOAD2 = NLOADW2 * 32;
 constexpr int NSPLITW2 = 8, NSPLIT2 = NSPLITW2 * 32;
-constexpr int NTHREADS2 = NLOAD2 + NSPLIT2 + 64;       // + the MMA warp + the weight-tile (TMA) warp
+constexpr int NTHREADS2 = NLOAD2 + NSPLIT2 + 96;       // + two MMA issuer warps + the weight-tile (TMA) warp
 constexpr int MMA_WARP2 = NLOADW2 + NSPLITW2;
 constexpr int TMA_WARP2 = MMA_WARP2 + 1;
 constexpr int LOOKAHEAD = 2;                     // cp.async groups a loader keeps in flight (< STAGES)
@@ -69,6 +69,7 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   auto tfree_bar = [&](int t) { return bars + 8u * (2 * C::STAGES + C::TST + t); };
   const uint32_t acc_bar = bars + 8u * (2 * C::STAGES + 2 * C::TST);
   const uint32_t tmem_slot = acc_bar + 8u;
+  auto turn_bar = [&](int i) { return acc_bar + 16u + 8u * i; };   // issuer i may issue its next k-block
   auto a_smem = [&](int s) { return base + s * C::STAGE; };
   auto b_raw = [&](int s) { return base + s * C::STAGE + A_TILE; };
   auto b_lo = [&](int s) { return base + s * C::STAGE + A_TILE + C::B_TILE; };
@@ -140,7 +141,9 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       mbar_init(tfull_bar(t), NSPLITW2 / 2);
       mbar_init(tfree_bar(t), 1);
     }
-    mbar_init(acc_bar, 1);
+    mbar_init(acc_bar, 2);                       // both MMA issuers commit to it
+    mbar_init(turn_bar(0), 1);
+    mbar_init(turn_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_wlo) : "memory");
@@ -240,7 +243,7 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
                      : "r"(ar + (((uint32_t)jj ^ sw) << 4)));
       }
 #pragma unroll
-      for (int e = 0; e < 32; ++e) lo[e] = __float_as_uint(lo_part(__uint_as_float(hi[e])));
+      for (int e = 0; e < 32; e += 2) lo_part2(hi[e], hi[e + 1], lo[e], lo[e + 1]);
       // the warp is converged: once the low parts are computed every lane's loads have returned
       __syncwarp();
       if (elect_one()) mbar_arrive(sfree_bar(s));
@@ -377,9 +380,13 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       __syncwarp();
     }
   } else {
-    // ======================= MMA issuer =======================
+    // ======================= MMA issuers =======================
     // The whole warp walks the loop and waits on the barriers (converged); one lane issues.  A lone
     // lane looping while 31 lanes sit at a convergence barrier paid for it in hand-off latency.
+    // Two issuer warps take alternate k-blocks (see conv_tc3.cu): tcgen05.mma issue blocks until the pipe
+    // accepts it, so one issuer's barrier wait + fence + commits (~250 clk) left the pipe idle every k-block;
+    // a `turn` mbarrier keeps the issue order, and with it the summation order, fixed.
+    const int me = warp == MMA_WARP2 ? 0 : 1;
     const bool plain = (a.flags & 64) != 0 && (a.flags & 16) != 0;   // experiment: arrive without commit
     const bool tracing = trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -387,10 +394,11 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) |
                             ((uint32_t)(BM >> 4) << 24);                    // N = 2*BN: [W ; W_lo]
     const uint32_t d_corr = tmem_base + (uint32_t)C::ACC0;
-    for (int kb = 0; kb < nk; ++kb) {
+    for (int kb = me; kb < nk; kb += 2) {
       const int s = kb % C::STAGES, t = kb % C::TST;
       FD_TRACE(2, kb, 0);
       mbar_wait(tfull_bar(t), (kb / C::TST) & 1);
+      if (kb > 0) mbar_wait(turn_bar(me), ((kb - 1) >> 1) & 1);   // the other issuer has issued k-block kb-1
       FD_TRACE(2, kb, 1);
       tc_fence_after();
       FD_TRACE(2, kb, 2);
@@ -423,6 +431,7 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
             if (!(a.flags & 16)) umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
           }
         }
+        mbar_arrive(turn_bar(me ^ 1));
         if (plain) {
           mbar_arrive(sfree_bar(s));
           mbar_arrive(tfree_bar(t));
@@ -505,11 +514,13 @@ int dispatch_tc2(const TcArgs& a, cudaStream_t st) {
 
 extern "C" int fd_debug_set_conv_trace(void* device_buffer) {
   // device_buffer: (3 * 256 * 4 + 8) int64 slots, or NULL to switch tracing off
+  fd::g_conv_trace_host = (long long*)device_buffer;
   cudaError_t e = cudaMemcpyToSymbol(g_trace, &device_buffer, sizeof(void*));
   return e == cudaSuccess ? 0 : 1;
 }
 
 namespace fd {
+long long* g_conv_trace_host = nullptr;
 int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st) {
   return mode == 0 ? dispatch_tc2<0>(a, st) : dispatch_tc2<1>(a, st);
 }

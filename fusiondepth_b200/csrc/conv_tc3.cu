@@ -18,7 +18,14 @@
 //   warps 0-3   weight splitters   W tile (TMA) -> W_lo tile next to it, fence.proxy.async, `wready`
 //   warps 4-11  A splitters        two groups on alternate k-blocks: patch row -> registers -> A / A_lo into the
 //                                  TMEM ring (tcgen05.st); then the epilogue (shared with conv_tc2's layout)
-//   warp 12     MMA issue          tcgen05.mma kind::tf32, A from TMEM, B = [W ; W_lo] from shared memory
+//   warps 12,15 MMA issue          tcgen05.mma kind::tf32, A from TMEM, B = [W ; W_lo] from shared memory.  Two
+//                                  issuers on alternate k-blocks: the role trace (tools/trace_conv3.py) showed
+//                                  one issuer spending ~400 clk per k-block in its two mbarrier waits (~90 clk
+//                                  each even when complete), fences and commits with the tensor pipe idle,
+//                                  because tcgen05.mma issue blocks until the pipe accepts it (862 clk per
+//                                  k-block against 384 of MMAs at BN=64, 1200 against 768 at BN=128).  The
+//                                  other issuer does its waits meanwhile; a `turn` mbarrier keeps the issue
+//                                  order (and with it the summation order) fixed.
 //   warp 13     W tiles by TMA     one k-block per stage
 //   warp 14     patches by TMA     one 32-channel chunk per buffer, a whole chunk ahead
 //
@@ -31,46 +38,59 @@ constexpr int T3_WSPLITW = 4, T3_ASPLITW = 8;
 constexpr int T3_MMA_WARP = T3_WSPLITW + T3_ASPLITW;        // 12
 constexpr int T3_WTMA_WARP = T3_MMA_WARP + 1;               // 13
 constexpr int T3_PTMA_WARP = T3_MMA_WARP + 2;               // 14
-constexpr int T3_NTHREADS = (T3_PTMA_WARP + 1) * 32;        // 480
+constexpr int T3_MMA2_WARP = T3_MMA_WARP + 3;               // 15: second MMA issuer (odd k-blocks)
+constexpr int T3_NTHREADS = (T3_MMA2_WARP + 1) * 32;        // 512
 constexpr int PBOX = 64;                                    // patch rows per TMA box
+// Timing experiment (fd_debug_set_conv_trace + tools/trace_conv.py): CTA (0,0) stamps clock64() at the hand-off
+// points of one lane per role into trace[role][k-block][4], kernel phases behind them.
+constexpr int T3_TRACE_KB = 256;
+#define T3_TRACE(role, kb, slot)                                                                   \
+  do {                                                                                             \
+    if (tracing && (kb) < T3_TRACE_KB) a.trace[((role) * T3_TRACE_KB + (kb)) * 4 + (slot)] = clock64(); \
+  } while (0)
 
 template <int BN>
 struct Cfg3 {
   static constexpr int B_TILE = BN * 128;
   static constexpr int WSTAGE = 2 * B_TILE;                             // [W ; W_lo]
-  static constexpr int STAGES = BN == 128 ? 3 : 4;
-  static constexpr int PROWS = BN == 128 ? 384 : 512;                   // rows per patch buffer
-  static constexpr int PATCH = PROWS * 128;
+  // The patch buffers are sized per launch (rows the layer's tiles need, in whole TMA boxes) and the rest of
+  // the 227 KB goes to W stages: the trace showed the issuers waiting for W once they no longer waited for each
+  // other (stage turn-around = MMAs done -> TMA from L2 -> W_lo split, ~2000 clk, against 3 stages x ~800 clk).
+  static constexpr int MAXST = 8;
+  static constexpr int MISC = 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row table*/ + 1024 /*CTA channel sums*/;
+  static constexpr int SMEM_MAX = 232448;
   static constexpr int TST = BN == 128 ? 2 : (BN == 64 ? 3 : 4);        // TMEM A-ring slots
   static constexpr int ACC0 = TST * 64;
   static constexpr bool PAIR = BN <= 64;
   static constexpr int NMAIN_ = PAIR ? (512 - ACC0 - BN) / (2 * BN) : (512 - ACC0) / BN - 1;
   static constexpr int NMAIN = NMAIN_ > 7 ? 7 : NMAIN_;
-  static constexpr int SMEM = 2 * PATCH + STAGES * WSTAGE + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*row table*/ +
-                              1024 /*CTA channel sums*/;
 };
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(T3_NTHREADS, 1)
 conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
-                const __grid_constant__ CUtensorMap tm_y) {
+                const __grid_constant__ CUtensorMap tm_y, const int patch_rows, const int nstages) {
   using C = Cfg3<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  auto patch = [&](int b) { return base + (uint32_t)b * C::PATCH; };
-  const uint32_t wbase = base + 2u * C::PATCH;
+  const uint32_t patch_bytes = (uint32_t)patch_rows * 128u;
+  auto patch = [&](int b) { return base + (uint32_t)b * patch_bytes; };
+  const uint32_t wbase = base + 2u * patch_bytes;
   auto b_raw = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE; };
   auto b_lo = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE + C::B_TILE; };
-  const uint32_t bars = wbase + C::STAGES * C::WSTAGE;
+  const uint32_t bars = wbase + (uint32_t)nstages * C::WSTAGE;
   auto wland_bar = [&](int s) { return bars + 8u * s; };                        // W tile landed (TMA tx)
-  auto wready_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };         // W_lo written
-  auto wfree_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };      // MMAs done with the stage
-  auto tfull_bar = [&](int t) { return bars + 8u * (3 * C::STAGES + t); };
-  auto tfree_bar = [&](int t) { return bars + 8u * (3 * C::STAGES + C::TST + t); };
-  auto pfull_bar = [&](int b) { return bars + 8u * (3 * C::STAGES + 2 * C::TST + b); };
-  auto pfree_bar = [&](int b) { return bars + 8u * (3 * C::STAGES + 2 * C::TST + 2 + b); };
-  const uint32_t acc_bar = bars + 8u * (3 * C::STAGES + 2 * C::TST + 4);
+  auto wready_bar = [&](int s) { return bars + 8u * (C::MAXST + s); };          // W_lo written
+  auto wfree_bar = [&](int s) { return bars + 8u * (2 * C::MAXST + s); };       // MMAs done with the stage
+  auto tfull_bar = [&](int t) { return bars + 8u * (3 * C::MAXST + t); };
+  auto tfree_bar = [&](int t) { return bars + 8u * (3 * C::MAXST + C::TST + t); };
+  auto pfull_bar = [&](int b) { return bars + 8u * (3 * C::MAXST + 2 * C::TST + b); };
+  auto pfree_bar = [&](int b) { return bars + 8u * (3 * C::MAXST + 2 * C::TST + 2 + b); };
+  const uint32_t acc_bar = bars + 8u * (3 * C::MAXST + 2 * C::TST + 4);
+  // W-stage ring position of a role: (stage, phase parity), advanced without divisions
+  auto ring_next = [&](int& st, uint32_t& ph) { if (++st == nstages) { st = 0; ph ^= 1u; } };
   const uint32_t tmem_slot = acc_bar + 8u;
+  auto turn_bar = [&](int i) { return acc_bar + 48u + 8u * i; };          // issuer i may issue its next k-block
   const uint32_t pinfo = acc_bar + 16u;                   // [0] patch start (pixel index), [1] patch rows needed
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -86,11 +106,16 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   const int nchunk = a.Cg / BK;
   const int nk = taps * nchunk;
   const int span = (a.KH - 1) * a.Wg + (a.KW - 1);        // largest tap shift
+  const bool ktrace = a.trace && blockIdx.x == 0 && blockIdx.y == 0;
+  if (ktrace && tid == T3_WSPLITW * 32) a.trace[3 * T3_TRACE_KB * 4 + 0] = clock64();
 
   // Row table: tile row r -> (pixel index of its tap-(0,0) source, valid-tap mask); per-warp min / max of the
   // pixel index in pinfo[0..3] / pinfo[4..7]
   const uint32_t tab_lin = bars + 512u, tab_mask = tab_lin + 4u * BM;
   const uint32_t cta_sums = tab_mask + 4u * BM;            // [2][BN] floats, only with a.stats
+  const uint32_t zero_row = bars + 384u;                   // 128 B of zeros: the "row" a padding tap reads
+  if (tid >= 256 && tid < 288)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(zero_row + 4u * (uint32_t)(tid - 256)), "r"(0u) : "memory");
   if (a.stats && tid >= BM && tid < BM + 2 * BN)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(tid - BM)), "f"(0.f) : "memory");
   if (tid < BM) {
@@ -128,7 +153,7 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   }
 
   if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(wland_bar(s), 1);
       mbar_init(wready_bar(s), T3_WSPLITW);
       mbar_init(wfree_bar(s), 1);
@@ -141,7 +166,9 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       mbar_init(pfull_bar(b), 1);
       mbar_init(pfree_bar(b), taps == 1 ? T3_ASPLITW / 2 : T3_ASPLITW);   // 1x1: a chunk belongs to one group
     }
-    mbar_init(acc_bar, 1);
+    mbar_init(acc_bar, 2);                                  // both MMA issuers commit to it
+    mbar_init(turn_bar(0), 1);
+    mbar_init(turn_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
@@ -154,6 +181,7 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (ktrace && tid == T3_WSPLITW * 32) a.trace[3 * T3_TRACE_KB * 4 + 1] = clock64();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   int lin_min = 0x7fffffff, lin_max = (int)0x80000000;
@@ -172,9 +200,12 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   if (warp < T3_WSPLITW) {
     // ======================= weight splitters: W_lo = W - tf32(W) in shared memory =======================
     constexpr int NV = C::B_TILE / 16 / (T3_WSPLITW * 32);          // float4 per thread per stage (>= 1 for BN >= 16)
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % C::STAGES;
-      mbar_wait(wland_bar(s), (kb / C::STAGES) & 1);
+    int s = 0;
+    uint32_t sph = 0;
+    const bool tracing = ktrace && tid == 0;
+    for (int kb = 0; kb < nk; ++kb, ring_next(s, sph)) {
+      mbar_wait(wland_bar(s), sph);
+      T3_TRACE(2, kb, 2);
       if (!(a.flags & 0x800)) {
 #pragma unroll
         for (int i = 0; i < (NV > 0 ? NV : 1); ++i) {
@@ -193,6 +224,7 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       }
       __syncwarp();
       if (elect_one()) mbar_arrive(wready_bar(s));
+      T3_TRACE(2, kb, 3);
     }
   } else if (warp < T3_MMA_WARP) {
     // ======================= A splitters, then epilogue =======================
@@ -207,9 +239,20 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     // patch row of this tile row's tap (0,0); rows past the image stay inside the buffer and are masked to zero
     const int pr0 = (vm >> 31) ? lin - pstart : (MODE == 0 ? 0 : span);
     int chunk_seen = -1;
+    const bool tracing = ktrace && lane == 0 && q == 0 && half == 0;
+    const int trole = 0;
+    // (chunk, kh, kw) of this group's k-block, stepped two taps at a time: no divisions in the loop (the trace
+    // put load + split at ~820 clk per k-block, ~200 instructions of which two runtime divisions, 32 selects
+    // for the padding mask and 64 for the low-order parts)
+    int c = half / taps, kh, kw;
+    {
+      const int tap0 = half - c * taps;
+      kh = tap0 / a.KW;
+      kw = tap0 - kh * a.KW;
+    }
     for (int kb = half; kb < nk; kb += 2) {
-      const int c = kb / taps, tap = kb - c * taps;
-      const int kh = tap / a.KW, kw = tap - kh * a.KW;
+      T3_TRACE(trole, kb, 0);
+      const int tap = kh * a.KW + kw;
       const int t = kb % C::TST, pb = c & 1;
       if (c != chunk_seen) {
         mbar_wait(pfull_bar(pb), (c >> 1) & 1);
@@ -219,7 +262,8 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       const uint32_t pr = (uint32_t)(MODE == 0 ? pr0 + sh : pr0 - sh);
       const bool ok = ((vm >> kh) & (vm >> (8 + kw)) & 1u) != 0;
       uint32_t hi[32], lo[32];
-      const uint32_t ar = patch(pb) + pr * 128u;
+      // padding taps read a row of zeros instead of being masked element by element
+      const uint32_t ar = ok ? patch(pb) + pr * 128u : zero_row;
       const uint32_t sw = pr & 7u;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
@@ -228,17 +272,22 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
                      : "r"(ar + (((uint32_t)jj ^ sw) << 4)));
       }
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        hi[e] = ok ? hi[e] : 0u;
-        lo[e] = __float_as_uint(lo_part(__uint_as_float(hi[e])));
-      }
+      for (int e = 0; e < 32; e += 2) lo_part2(hi[e], hi[e + 1], lo[e], lo[e + 1]);
       __syncwarp();
       // last k-block of this chunk for this warp: its reads of the patch are complete
-      if (kb + 2 >= (c + 1) * taps && elect_one()) mbar_arrive(pfree_bar(pb));
+      if (tap + 2 >= taps && elect_one()) mbar_arrive(pfree_bar(pb));
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (++kw == a.KW) {
+          kw = 0;
+          if (++kh == a.KH) { kh = 0; ++c; }
+        }
+      T3_TRACE(trole, kb, 1);
       if (kb >= C::TST) {
         mbar_wait(tfree_bar(t), ((kb / C::TST) - 1) & 1);
         tc_fence_after();
       }
+      T3_TRACE(trole, kb, 2);
       const uint32_t tcol = tlane + (uint32_t)(t * 64);
       tmem_st16(tcol, *reinterpret_cast<const uint32_t(*)[16]>(&hi[0]));
       tmem_st16(tcol + 16u, *reinterpret_cast<const uint32_t(*)[16]>(&hi[16]));
@@ -250,10 +299,12 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       tc_fence_before();
       __syncwarp();
       if (elect_one()) mbar_arrive(tfull_bar(t));
+      T3_TRACE(trole, kb, 3);
     }
     // ---- epilogue: warp (q, half) owns rows 32q..32q+31 and the 16-column chunks half, half+2, ... ----
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    if (ktrace && tid == T3_WSPLITW * 32) a.trace[3 * T3_TRACE_KB * 4 + 2] = clock64();
     const long m = m0 + row;
     const bool row_ok = row < rows_valid;
     const uint32_t trow = tlane + (uint32_t)C::ACC0;
@@ -342,11 +393,16 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         if (ch < a.N) atomicAdd(a.stats + (long)stat * a.N + ch, (double)v);
       }
     }
+    if (ktrace && tid == T3_WSPLITW * 32) a.trace[3 * T3_TRACE_KB * 4 + 3] = clock64();
   } else if (warp == T3_WTMA_WARP) {
     // ======================= W tiles by TMA =======================
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % C::STAGES;
-      if (kb >= C::STAGES) mbar_wait(wfree_bar(s), ((kb / C::STAGES) - 1) & 1);
+    int s = 0;
+    uint32_t sph = 0;
+    const bool tracing = ktrace && lane == 0;
+    for (int kb = 0; kb < nk; ++kb, ring_next(s, sph)) {
+      T3_TRACE(2, kb, 0);
+      if (kb >= nstages) mbar_wait(wfree_bar(s), sph ^ 1u);
+      T3_TRACE(2, kb, 1);
       if (elect_one()) {
         const int c = kb / taps, tap = kb - c * taps;
         mbar_expect_tx(wland_bar(s), C::B_TILE);
@@ -374,11 +430,20 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) |
                             ((uint32_t)(BM >> 4) << 24);                    // N = 2*BN: [W ; W_lo]
     const uint32_t d_corr = tmem_base + (uint32_t)C::ACC0;
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % C::STAGES, t = kb % C::TST;
-      mbar_wait(wready_bar(s), (kb / C::STAGES) & 1);
+    const bool tracing = ktrace && lane == 0;
+    const int me = warp == T3_MMA_WARP ? 0 : 1;             // issuer 0: even k-blocks, issuer 1: odd
+    int s = 0;
+    uint32_t sph = 0;
+    if (me) ring_next(s, sph);
+    for (int kb = me; kb < nk; kb += 2, ring_next(s, sph), ring_next(s, sph)) {
+      const int t = kb % C::TST;
+      T3_TRACE(1, kb, 0);
+      mbar_wait(wready_bar(s), sph);
+      T3_TRACE(1, kb, 1);
       mbar_wait(tfull_bar(t), (kb / C::TST) & 1);
+      if (kb > 0) mbar_wait(turn_bar(me), ((kb - 1) >> 1) & 1);   // the other issuer has issued k-block kb-1
       tc_fence_after();
+      T3_TRACE(1, kb, 2);
       if (elect_one()) {
         const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
         const uint32_t ta = tmem_base + (uint32_t)(t * 64), tal = ta + 32u;
@@ -405,20 +470,41 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
             umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
           }
         }
+        mbar_arrive(turn_bar(me ^ 1));
         umma_commit(wfree_bar(s));
         umma_commit(tfree_bar(t));
       }
       __syncwarp();
+      T3_TRACE(1, kb, 3);
     }
     if (elect_one()) umma_commit(acc_bar);
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
+  if (ktrace && tid == T3_WSPLITW * 32) a.trace[3 * T3_TRACE_KB * 4 + 4] = clock64();
   if (warp == T3_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
+}
+
+// worst-case number of patch rows a 128-pixel tile (inside one image) needs: its own raster span in the gathered
+// tensor (every output-row change drifts by |Wg - Wo| pixels) + the tap span, in whole TMA boxes
+int patch_rows_needed(const TcArgs& a) {
+  const long dW = a.Wg > a.Wo ? a.Wg - a.Wo : a.Wo - a.Wg;
+  const long row_changes = (BM - 2) / a.Wo + 1;
+  const long need = (BM - 1) + dW * row_changes + (long)(a.KH - 1) * a.Wg + a.KW;
+  const long rows = (need + PBOX - 1) / PBOX * PBOX;
+  return rows > 4096 ? -1 : (int)rows;
+}
+// W stages that fit next to two patch buffers of `prows` rows
+template <int BN>
+int stages_for(int prows) {
+  using C = Cfg3<BN>;
+  const int left = C::SMEM_MAX - C::MISC - 2 * prows * 128;
+  const int n = left / C::WSTAGE;
+  return n > C::MAXST ? C::MAXST : n;
 }
 
 template <int BN, int MODE>
@@ -427,13 +513,16 @@ int launch_tc3(const TcArgs& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM);
+                                         C::SMEM_MAX);
     if (e != cudaSuccess) {
-      fd::set_error("conv_tc3: cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
+      fd::set_error("conv_tc3: cannot reserve %d B of shared memory: %s", C::SMEM_MAX, cudaGetErrorString(e));
       return 1;
     }
     configured = true;
   }
+  const int prows = patch_rows_needed(a);
+  const int nstages = stages_for<BN>(prows);
+  const int smem = 2 * prows * 128 + nstages * C::WSTAGE + C::MISC;
   CUtensorMap tw, tx;
   int rc = make_map_2d(&tw, a.w, a.N, a.K, BN);
   if (rc) return rc;
@@ -445,26 +534,25 @@ int launch_tc3(const TcArgs& a, cudaStream_t st) {
     if (rc) return rc;
   }
   dim3 grid(a.B * fd::cdiv((long)a.Ho * a.Wo, BM), fd::cdiv(a.N, BN));
-  conv_tc3_kernel<BN, MODE><<<grid, T3_NTHREADS, C::SMEM, st>>>(a, tw, tx, ty);
+  conv_tc3_kernel<BN, MODE><<<grid, T3_NTHREADS, smem, st>>>(a, tw, tx, ty, prows, nstages);
   FD_CHECK_LAUNCH();
   return 0;
 }
 
 template <int BN>
 bool patch_fits(const TcArgs& a) {
-  // worst-case number of patch rows a 128-pixel tile (inside one image) needs: its own raster span in the
-  // gathered tensor (every output-row change drifts by |Wg - Wo| pixels) + the tap span, in whole TMA boxes
-  const long dW = a.Wg > a.Wo ? a.Wg - a.Wo : a.Wo - a.Wg;
-  const long row_changes = (BM - 2) / a.Wo + 1;
-  const long need = (BM - 1) + dW * row_changes + (long)(a.KH - 1) * a.Wg + a.KW;
-  return (need + PBOX - 1) / PBOX * PBOX <= Cfg3<BN>::PROWS;
+  const int prows = patch_rows_needed(a);
+  // the epilogue stages the output tile (BN * 512 B) over the patch buffers and, past them, the W stages
+  return prows > 0 && stages_for<BN>(prows) >= 3;
 }
 
 }  // namespace
 
 namespace fd {
 // returns -1 when this variant does not take the problem (the caller falls back to conv_tc2)
-int conv_tc3_dispatch(const TcArgs& a, int mode, cudaStream_t st) {
+int conv_tc3_dispatch(const TcArgs& a0, int mode, cudaStream_t st) {
+  TcArgs a = a0;
+  a.trace = g_conv_trace_host;
   if (a.stride != 1 || a.Cg % BK != 0 || a.KH > 8 || a.KW > 8 || a.M >= (1L << 31)) return -1;
   if ((long)a.B * a.Hg * a.Wg >= (1L << 31) - 65536) return -1;
   if ((((uintptr_t)a.w | (uintptr_t)a.x | (uintptr_t)a.y) & 15) != 0) return -1;

@@ -1,0 +1,546 @@
+// Implicit-GEMM convolution (forward / data gradient, stride 1) on tcgen05 -- the PERSISTENT variant of
+// conv_tc3.cu for launches with more tiles than SMs (the 64-channel layers at 1/4 resolution: 360 tiles).
+//
+// Same contract, numerics and data path as conv_tc3 (3xTF32, input patch by TMA once per 32-channel chunk, A
+// operand split into tensor memory, W_lo computed in shared memory, two MMA issuers).  What changes is the
+// schedule.  The role trace of conv_tc3 on the layer-1 shape (tools/trace_conv3.py) put a CTA at ~19.4 k cycles
+// of which only ~10.2 k are the 18 k-blocks of main loop: ~4.1 k pass before the first MMA (barrier / TMEM
+// set-up, ~1.3 k cycles of TMA latency for the first patch and W tile, first split) and ~4.4 k in the epilogue
+// (TMEM reads at 64 B/clk, bias / activation / statistics, stores), and 360 one-tile CTAs on 148 SMs run as 3
+// waves although the work is 2.43.  Here one CTA per SM walks tiles T = blockIdx.x, + gridDim.x, ...:
+//
+//   * every pipeline (W stages, TMEM A-ring, patch double buffer, issuer turn) runs on across tile boundaries --
+//     the producers are already fetching and splitting tile i+1 while tile i's last MMAs execute;
+//   * the epilogue has its own four warps; the accumulators are double-buffered in tensor memory for BN <= 64
+//     (2 x [corr | main | corr2]), so tile i drains while tile i+1 accumulates.  BN = 128 has tensor memory for
+//     one set only: its issuers wait for the drain (the TMEM reads), not for the stores;
+//   * tiles are dealt round-robin, so an SM does 2 or 3 tiles back to back without a launch gap.
+//
+// With one accumulator per product class for BN <= 64 (no rotation) the longest chain of truncating tensor-core
+// accumulations is K = 1152 here; measured error vs fp64 stays below the 1e-5 bound of the parity tests.
+//
+// Roles (640 threads): warps 0-3 W_lo splitters, 4-11 A splitters (two groups on alternate k-blocks), 12 / 15 MMA
+// issuers (even / odd k-blocks), 13 W tiles by TMA, 14 patches by TMA, 16-19 epilogue.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int T4_WSPLITW = 4, T4_ASPLITW = 8;
+constexpr int T4_MMA_WARP = T4_WSPLITW + T4_ASPLITW;        // 12
+constexpr int T4_WTMA_WARP = 13, T4_PTMA_WARP = 14, T4_MMA2_WARP = 15;
+constexpr int T4_EPI_WARP0 = 16, T4_EPIW = 4;
+constexpr int T4_NTHREADS = (T4_EPI_WARP0 + T4_EPIW) * 32;  // 640
+constexpr int PBOX4 = 64;                                   // patch rows per TMA box
+
+template <int BN>
+struct Cfg4 {
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int WSTAGE = 2 * B_TILE;                             // [W ; W_lo]
+  static constexpr int MAXST = 8;
+  static constexpr int MISC = 1024 /*align*/ + 512 /*barriers, zero row*/ + 1024 /*CTA channel sums*/;
+  static constexpr int SMEM_MAX = 232448;
+  static constexpr int TST = 2;                                         // TMEM A-ring slots: one per splitter group
+  static constexpr int ACC0 = TST * 64;
+  static constexpr bool PAIR = BN <= 64;
+  static constexpr int NSETS = BN <= 64 ? 2 : 1;                        // accumulator sets in tensor memory
+  static constexpr int NMAIN = BN <= 64 ? 1 : 2;
+  static constexpr int SETCOLS = PAIR ? BN + NMAIN * 2 * BN : (1 + NMAIN) * BN;
+  static_assert(ACC0 + NSETS * SETCOLS <= 512, "tensor memory");
+};
+
+struct Tile4 {
+  int img, r0, n0, rows_valid;
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(T4_NTHREADS, 1)
+conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                const int patch_rows, const int nstages, const int gx, const int total_tiles) {
+  using C = Cfg4<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t patch_bytes = (uint32_t)patch_rows * 128u;
+  auto patch = [&](int b) { return base + (uint32_t)b * patch_bytes; };
+  const uint32_t wbase = base + 2u * patch_bytes;
+  auto b_raw = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE; };
+  auto b_lo = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE + C::B_TILE; };
+  const uint32_t bars = wbase + (uint32_t)nstages * C::WSTAGE;
+  auto wland_bar = [&](int s) { return bars + 8u * s; };                        // W tile landed (TMA tx)
+  auto wready_bar = [&](int s) { return bars + 8u * (C::MAXST + s); };          // W_lo written
+  auto wfree_bar = [&](int s) { return bars + 8u * (2 * C::MAXST + s); };       // MMAs done with the stage
+  auto tfull_bar = [&](int t) { return bars + 8u * (24 + t); };                 // A / A_lo of a k-block in TMEM
+  auto tfree_bar = [&](int t) { return bars + 8u * (26 + t); };
+  auto pfull_bar = [&](int b) { return bars + 8u * (28 + b); };                 // patch buffer landed
+  auto pfree_bar = [&](int b) { return bars + 8u * (30 + b); };
+  auto accfull_bar = [&](int s) { return bars + 8u * (32 + s); };               // a tile's MMAs are complete
+  auto accfree_bar = [&](int s) { return bars + 8u * (34 + s); };               // the epilogue has read the set
+  auto turn_bar = [&](int i) { return bars + 8u * (36 + i); };                  // issuer i may issue
+  const uint32_t tmem_slot = bars + 8u * 38;
+  const uint32_t pinfo = bars + 8u * 39;                    // [2] patch start (pixel index) of the chunk in buffer b
+  const uint32_t zero_row = bars + 384u;                    // 128 B of zeros: the "row" a padding tap reads
+  const uint32_t cta_sums = bars + 512u;                    // [2][BN] floats, only with a.stats
+  auto ring_next = [&](int& st, uint32_t& ph) { if (++st == nstages) { st = 0; ph ^= 1u; } };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Tiles never cross an image (see conv_tc3.cu).  Tile id T -> (m tile x, n tile y), x fastest.
+  const int HoWo = a.Ho * a.Wo;
+  const int tpi = (HoWo + BM - 1) / BM;
+  const int taps = a.KH * a.KW;
+  const int nchunk = a.Cg / BK;
+  const int nk = taps * nchunk;
+  const int span = (a.KH - 1) * a.Wg + (a.KW - 1);         // largest tap shift
+  auto tile_of = [&](int T) {
+    Tile4 t;
+    const int y = T / gx, x = T - y * gx;
+    t.img = x / tpi;
+    t.r0 = (x - t.img * tpi) * BM;
+    t.n0 = y * BN;
+    t.rows_valid = HoWo - t.r0 < BM ? HoWo - t.r0 : BM;
+    return t;
+  };
+  // tile row -> (pixel index of its tap-(0,0) source, valid-tap mask); bit 31 of the mask = the row exists
+  auto row_geom = [&](const Tile4& t, int row, int& lin, uint32_t& mask) {
+    lin = 0;
+    mask = 0;
+    if (row < t.rows_valid) {
+      const int r = t.r0 + row;
+      const int ho = r / a.Wo, wo = r - ho * a.Wo;
+      int hq, wq;
+      if (MODE == 0) {
+        hq = ho - a.pad; wq = wo - a.pad;
+        for (int u = 0; u < a.KH; ++u) mask |= (uint32_t)(hq + u >= 0 && hq + u < a.Hg) << u;
+        for (int u = 0; u < a.KW; ++u) mask |= (uint32_t)(wq + u >= 0 && wq + u < a.Wg) << (8 + u);
+      } else {
+        hq = ho + a.pad; wq = wo + a.pad;
+        for (int u = 0; u < a.KH; ++u) mask |= (uint32_t)(hq - u >= 0 && hq - u < a.Hg) << u;
+        for (int u = 0; u < a.KW; ++u) mask |= (uint32_t)(wq - u >= 0 && wq - u < a.Wg) << (8 + u);
+      }
+      lin = (t.img * a.Hg + hq) * a.Wg + wq;
+      mask |= 1u << 31;
+    }
+  };
+
+  if (tid >= 256 && tid < 288)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(zero_row + 4u * (uint32_t)(tid - 256)), "r"(0u) : "memory");
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(wland_bar(s), 1);
+      mbar_init(wready_bar(s), T4_WSPLITW);
+      mbar_init(wfree_bar(s), 1);
+    }
+    for (int t = 0; t < C::TST; ++t) {
+      mbar_init(tfull_bar(t), T4_ASPLITW / 2);
+      mbar_init(tfree_bar(t), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(pfull_bar(b), 1);
+      mbar_init(pfree_bar(b), taps == 1 ? T4_ASPLITW / 2 : T4_ASPLITW);   // 1x1: a chunk belongs to one group
+      mbar_init(accfull_bar(b), 2);                                        // both MMA issuers commit to it
+      mbar_init(accfree_bar(b), T4_EPIW);
+      mbar_init(turn_bar(b), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+  }
+  if (warp == T4_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < T4_WSPLITW) {
+    // ======================= weight splitters: W_lo = W - tf32(W) in shared memory =======================
+    constexpr int NV = C::B_TILE / 16 / (T4_WSPLITW * 32);          // float4 per thread per stage
+    int s = 0;
+    uint32_t sph = 0;
+    for (int T = blockIdx.x; T < total_tiles; T += gridDim.x) {
+      for (int kb = 0; kb < nk; ++kb, ring_next(s, sph)) {
+        mbar_wait(wland_bar(s), sph);
+        if (!(a.flags & 0x800)) {
+#pragma unroll
+          for (int i = 0; i < (NV > 0 ? NV : 1); ++i) {
+            const uint32_t idx = (uint32_t)(tid + T4_WSPLITW * 32 * i);
+            if (idx < (uint32_t)(C::B_TILE / 16)) {
+              float4 v;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                           : "r"(b_raw(s) + idx * 16u));
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(b_lo(s) + idx * 16u), "f"(lo_part(v.x)),
+                           "f"(lo_part(v.y)), "f"(lo_part(v.z)), "f"(lo_part(v.w))
+                           : "memory");
+            }
+          }
+          fence_async_proxy();
+        }
+        __syncwarp();
+        if (elect_one()) mbar_arrive(wready_bar(s));
+      }
+    }
+  } else if (warp < T4_MMA_WARP) {
+    // ======================= A splitters: group `half` takes the k-blocks g with g % 2 == half =======================
+    // (g counts k-blocks over all of this CTA's tiles; TMEM slot = half)
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - T4_WSPLITW) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    int gbase = 0, gcb = 0;                       // k-blocks / chunks of the earlier tiles
+    uint32_t nuse = 0;                            // uses of this group's TMEM slot so far
+    for (int T = blockIdx.x; T < total_tiles; T += gridDim.x, gbase += nk, gcb += nchunk) {
+      const Tile4 tl = tile_of(T);
+      int lin;
+      uint32_t vm;
+      row_geom(tl, row, lin, vm);
+      const int kb0 = (half - gbase) & 1;
+      int c = kb0 / taps, kh, kw;
+      {
+        const int tap0 = kb0 - c * taps;
+        kh = tap0 / a.KW;
+        kw = tap0 - kh * a.KW;
+      }
+      int chunk_seen = -1, pr0 = 0;
+      for (int kb = kb0; kb < nk; kb += 2, ++nuse) {
+        const int tap = kh * a.KW + kw;
+        const int gc = gcb + c, pb = gc & 1;
+        if (c != chunk_seen) {
+          mbar_wait(pfull_bar(pb), (uint32_t)(gc >> 1) & 1u);
+          if (chunk_seen < 0) {
+            int pstart;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pstart) : "r"(pinfo + 4u * (uint32_t)pb));
+            // rows past the image stay inside the buffer and read the zero row
+            pr0 = (vm >> 31) ? lin - pstart : (MODE == 0 ? 0 : span);
+          }
+          chunk_seen = c;
+        }
+        const int sh = kh * a.Wg + kw;
+        const uint32_t pr = (uint32_t)(MODE == 0 ? pr0 + sh : pr0 - sh);
+        const bool ok = ((vm >> kh) & (vm >> (8 + kw)) & 1u) != 0;
+        uint32_t hi[32], lo[32];
+        const uint32_t ar = ok ? patch(pb) + pr * 128u : zero_row;
+        const uint32_t sw = pr & 7u;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(hi[4 * jj]), "=r"(hi[4 * jj + 1]), "=r"(hi[4 * jj + 2]), "=r"(hi[4 * jj + 3])
+                       : "r"(ar + (((uint32_t)jj ^ sw) << 4)));
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) lo_part2(hi[e], hi[e + 1], lo[e], lo[e + 1]);
+        __syncwarp();
+        // last k-block of this chunk for this warp: its reads of the patch are complete
+        if (tap + 2 >= taps && elect_one()) mbar_arrive(pfree_bar(pb));
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (++kw == a.KW) {
+            kw = 0;
+            if (++kh == a.KH) { kh = 0; ++c; }
+          }
+        if (nuse >= 1) {
+          mbar_wait(tfree_bar(half), (nuse - 1u) & 1u);
+          tc_fence_after();
+        }
+        tmem_st16(tcol, *reinterpret_cast<const uint32_t(*)[16]>(&hi[0]));
+        tmem_st16(tcol + 16u, *reinterpret_cast<const uint32_t(*)[16]>(&hi[16]));
+        if (!(a.flags & 0x800)) {
+          tmem_st16(tcol + 32u, *reinterpret_cast<const uint32_t(*)[16]>(&lo[0]));
+          tmem_st16(tcol + 48u, *reinterpret_cast<const uint32_t(*)[16]>(&lo[16]));
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(tfull_bar(half));
+      }
+    }
+  } else if (warp == T4_WTMA_WARP) {
+    // ======================= W tiles by TMA =======================
+    int s = 0, g = 0;
+    uint32_t sph = 0;
+    for (int T = blockIdx.x; T < total_tiles; T += gridDim.x) {
+      const Tile4 tl = tile_of(T);
+      int c = 0, tap = 0;
+      for (int kb = 0; kb < nk; ++kb, ++g, ring_next(s, sph)) {
+        if (g >= nstages) mbar_wait(wfree_bar(s), sph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(wland_bar(s), C::B_TILE);
+          tma_load_2d(b_raw(s), &tm_w, tap * a.Cg + c * BK, tl.n0, wland_bar(s));
+        }
+        __syncwarp();
+        if (++tap == taps) { tap = 0; ++c; }
+      }
+    }
+  } else if (warp == T4_PTMA_WARP) {
+    // ======================= patches by TMA: chunk gc -> buffer gc & 1 =======================
+    int gc = 0;
+    for (int T = blockIdx.x; T < total_tiles; T += gridDim.x) {
+      const Tile4 tl = tile_of(T);
+      // pixel range the tile's rows start from (not always row 0 / the last row: a pad-0 data gradient steps
+      // back by one pixel at every output-row change)
+      int lo = 0x7fffffff, hi = (int)0x80000000;
+#pragma unroll
+      for (int i = 0; i < BM / 32; ++i) {
+        int lin;
+        uint32_t vm;
+        row_geom(tl, lane + 32 * i, lin, vm);
+        if (vm >> 31) { lo = min(lo, lin); hi = max(hi, lin); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      const int pstart = MODE == 0 ? lo : lo - span;
+      const int prows = hi - lo + span + 1;
+      const int nbox = (prows + PBOX4 - 1) / PBOX4;
+      for (int c = 0; c < nchunk; ++c, ++gc) {
+        const int pb = gc & 1;
+        if (gc >= 2) mbar_wait(pfree_bar(pb), (uint32_t)((gc >> 1) - 1) & 1u);
+        if (elect_one()) {
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(pinfo + 4u * (uint32_t)pb), "r"(pstart) : "memory");
+          mbar_expect_tx(pfull_bar(pb), (uint32_t)nbox * PBOX4 * 128u);
+          for (int i = 0; i < nbox; ++i)
+            tma_load_2d(patch(pb) + (uint32_t)i * PBOX4 * 128u, &tm_x, c * BK, pstart + i * PBOX4, pfull_bar(pb));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == T4_MMA_WARP || warp == T4_MMA2_WARP) {
+    // ======================= MMA issuers: issuer `me` takes the k-blocks g with g % 2 == me =======================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);                    // N = 2*BN: [W ; W_lo]
+    const int me = warp == T4_MMA_WARP ? 0 : 1;
+    int s = 0, gbase = 0, ti = 0;
+    uint32_t sph = 0, nuse = 0;
+    if (me) ring_next(s, sph);
+    for (int T = blockIdx.x; T < total_tiles; T += gridDim.x, gbase += nk, ++ti) {
+      const int set = ti % C::NSETS;
+      const uint32_t d_corr = tmem_base + (uint32_t)(C::ACC0 + set * C::SETCOLS);
+      if (ti >= C::NSETS) {                        // the epilogue has read this set's previous tile
+        mbar_wait(accfree_bar(set), (uint32_t)(ti / C::NSETS - 1) & 1u);
+        tc_fence_after();
+      }
+      for (int kb = (me - gbase) & 1; kb < nk; kb += 2, ++nuse, ring_next(s, sph), ring_next(s, sph)) {
+        const int g = gbase + kb;
+        mbar_wait(wready_bar(s), sph);
+        mbar_wait(tfull_bar(me), nuse & 1u);
+        if (g > 0) mbar_wait(turn_bar(me), (uint32_t)((g - 1) >> 1) & 1u);   // the other issuer has issued g-1
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
+          const uint32_t ta = tmem_base + (uint32_t)(me * 64), tal = ta + 32u;
+          if (a.flags & 0x800) {
+            const uint32_t d_main = d_corr + (uint32_t)(C::PAIR ? BN + (kb % C::NMAIN) * 2 * BN : (1 + kb % C::NMAIN) * BN);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_ts(d_main, ta + 8u * k, db + (uint64_t)(k * 32 >> 4), idesc, (kb >= C::NMAIN) || (k != 0));
+          } else if (C::PAIR) {
+            const uint32_t d_pair = d_corr + (uint32_t)(BN + (kb % C::NMAIN) * 2 * BN);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+              umma_tf32_ts(d_pair, ta + 8u * k, db + adv, idesc2, (kb >= C::NMAIN) || (k != 0));
+            }
+          } else {
+            const uint32_t d_main = d_corr + (uint32_t)((1 + kb % C::NMAIN) * BN);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
+              umma_tf32_ts(d_corr, ta + 8u * k, dbl + adv, idesc, 1);
+              umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
+            }
+          }
+          mbar_arrive(turn_bar(me ^ 1));
+          umma_commit(wfree_bar(s));
+          umma_commit(tfree_bar(me));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(accfull_bar(set));
+      __syncwarp();
+    }
+  } else {
+    // ======================= epilogue: warp q owns tile rows 32q .. 32q+31, all BN columns =======================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = tid - T4_EPI_WARP0 * 32;          // 0..127
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool single = (a.flags & 0x800) != 0;
+    const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
+    const int nacc = single ? nmain : (C::PAIR ? 2 * nmain + 1 : nmain + 1);
+    int ti = 0;
+    for (int T = blockIdx.x; T < total_tiles; T += gridDim.x, ++ti) {
+      const Tile4 tl = tile_of(T);
+      const int set = ti % C::NSETS;
+      const uint32_t trow = tlane + (uint32_t)(C::ACC0 + set * C::SETCOLS);
+      const long m = (long)tl.img * HoWo + tl.r0 + row;
+      const bool row_ok = row < tl.rows_valid;
+      if (a.stats) {
+        for (int i = et; i < 2 * BN; i += T4_EPIW * 32)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)i), "f"(0.f) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(T4_EPIW * 32) : "memory");
+      }
+      mbar_wait(accfull_bar(set), (uint32_t)(ti / C::NSETS) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        // accumulators in summation order: main, corr2 (PAIR) ..., then the A_lo * W correction
+        float acc[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+        for (int g = 0; g < nacc; g += 2) {
+          uint32_t v[2][16];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = g + u;
+            if (i < nacc) {
+              const int col = single ? (C::PAIR ? BN + 2 * i * BN : (1 + i) * BN)
+                                     : (i == nacc - 1 ? 0 : (C::PAIR ? BN + i * BN : (1 + i) * BN));
+              tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);
+            }
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (g + u < nacc) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(v[u][e]);
+            }
+          }
+        }
+        if (c + 16 >= BN) {
+          // every column of the set is in registers: the issuers may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (elect_one()) mbar_arrive(accfree_bar(set));
+        }
+        if (a.stats) {
+          // rows past the tile end hold exact zeros (zero A rows), so they add nothing
+          float s1[16], s2[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { s1[e] = acc[e]; s2[e] = acc[e] * acc[e]; }
+#pragma unroll
+          for (int width = 8, off = 16; width >= 1; width >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < width; ++i) {
+              const float send1 = up ? s1[i] : s1[i + width], send2 = up ? s2[i] : s2[i + width];
+              const float keep1 = up ? s1[i + width] : s1[i], keep2 = up ? s2[i + width] : s2[i];
+              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            }
+          }
+          s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+          s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+          if (!(lane & 1)) {
+            const int ch = c + ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)ch), "f"(s1[0]) : "memory");
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(BN + ch)), "f"(s2[0]) : "memory");
+          }
+        }
+        if (row_ok && tl.n0 + c < a.N) {
+          float o[16];
+          bias_act16(acc, a.bias ? a.bias + tl.n0 + c : nullptr, a.act, o);
+          float4* dst = reinterpret_cast<float4*>(a.y + m * a.N + tl.n0 + c);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+        }
+      }
+      if (a.stats) {
+        asm volatile("bar.sync 1, %0;" ::"n"(T4_EPIW * 32) : "memory");
+        for (int i = et; i < 2 * BN; i += T4_EPIW * 32) {
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cta_sums + 4u * (uint32_t)i));
+          const int stat = i / BN, ch = tl.n0 + (i - stat * BN);
+          if (ch < a.N) atomicAdd(a.stats + (long)stat * a.N + ch, (double)v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == T4_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// worst-case number of patch rows a 128-pixel tile (inside one image) needs, in whole TMA boxes (conv_tc3.cu)
+int patch_rows_needed4(const TcArgs& a) {
+  const long dW = a.Wg > a.Wo ? a.Wg - a.Wo : a.Wo - a.Wg;
+  const long row_changes = (BM - 2) / a.Wo + 1;
+  const long need = (BM - 1) + dW * row_changes + (long)(a.KH - 1) * a.Wg + a.KW;
+  const long rows = (need + PBOX4 - 1) / PBOX4 * PBOX4;
+  return rows > 4096 ? -1 : (int)rows;
+}
+template <int BN>
+int stages_for4(int prows) {
+  using C = Cfg4<BN>;
+  const int left = C::SMEM_MAX - C::MISC - 2 * prows * 128;
+  const int n = left / C::WSTAGE;
+  return n > C::MAXST ? C::MAXST : n;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int MODE>
+int launch_tc4(const TcArgs& a, cudaStream_t st) {
+  using C = Cfg4<BN>;
+  const int prows = patch_rows_needed4(a);
+  if (prows < 0) return -1;
+  const int nstages = stages_for4<BN>(prows);
+  if (nstages < 3) return -1;
+  const int gx = a.B * fd::cdiv((long)a.Ho * a.Wo, BM);
+  const int total = gx * fd::cdiv(a.N, BN);
+  const int sms = sm_count();
+  if (total <= sms) return -1;                 // one tile per CTA: nothing to overlap, conv_tc3 does it
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc4_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_MAX);
+    if (e != cudaSuccess) {
+      fd::set_error("conv_tc4: cannot reserve %d B of shared memory: %s", C::SMEM_MAX, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  CUtensorMap tw, tx;
+  int rc = make_map_2d(&tw, a.w, a.N, a.K, BN);
+  if (rc) return rc;
+  rc = make_map_2d(&tx, a.x, (long)a.B * a.Hg * a.Wg, a.Cg, PBOX4);
+  if (rc) return rc;
+  const int smem = 2 * prows * 128 + nstages * C::WSTAGE + C::MISC;
+  conv_tc4_kernel<BN, MODE><<<sms, T4_NTHREADS, smem, st>>>(a, tw, tx, prows, nstages, gx, total);
+  FD_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+namespace fd {
+// returns -1 when this variant does not take the problem (the caller falls back to conv_tc3 / conv_tc2)
+int conv_tc4_dispatch(const TcArgs& a, int mode, cudaStream_t st) {
+  if (a.stride != 1 || a.Cg % BK != 0 || a.KH > 8 || a.KW > 8 || a.M >= (1L << 31) || a.trace) return -1;
+  if ((long)a.B * a.Hg * a.Wg >= (1L << 31) - 65536) return -1;
+  if ((((uintptr_t)a.w | (uintptr_t)a.x | (uintptr_t)a.y) & 15) != 0) return -1;
+  if (a.N % 128 == 0) return mode == 0 ? launch_tc4<128, 0>(a, st) : launch_tc4<128, 1>(a, st);
+  if (a.N % 64 == 0) return mode == 0 ? launch_tc4<64, 0>(a, st) : launch_tc4<64, 1>(a, st);
+  if (a.N % 32 == 0) return mode == 0 ? launch_tc4<32, 0>(a, st) : launch_tc4<32, 1>(a, st);
+  return -1;
+}
+}  // namespace fd

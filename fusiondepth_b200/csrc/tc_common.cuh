@@ -19,12 +19,18 @@ struct TcArgs {
   int K;
   int flags;          // conv_tc2: bit 0 = loader signals `landed` per warp through cp.async groups
   double* stats;      // conv_tc2 forward, optional: [2][N] per-channel sum / sum of squares of y (+=)
+  long long* trace;   // timing experiment (fd_debug_set_conv_trace): clock64() stamps of CTA (0,0), else null
 };
+// device buffer registered by fd_debug_set_conv_trace (conv_tc2.cu), or null
+extern long long* g_conv_trace_host;
 // conv_tc2.cu: A-operand-in-TMEM kernels (mode 0 forward, 1 data gradient)
 int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st);
 // conv_tc3.cu: the same with the input patch fetched once per 32-channel chunk by TMA and W_lo computed in
 // shared memory (stride-1 layers whose patch fits); returns -1 when it does not take the problem
 int conv_tc3_dispatch(const TcArgs& a, int mode, cudaStream_t st);
+// conv_tc4.cu: persistent variant of conv_tc3 (epilogue overlapped with the next tile) for launches with more
+// tiles than SMs; returns -1 when it does not take the problem
+int conv_tc4_dispatch(const TcArgs& a, int mode, cudaStream_t st);
 }  // namespace fd
 
 namespace {
@@ -183,6 +189,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&o)[16]) {
 }
 __device__ __forceinline__ float lo_part(float v) {
   return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+}
+
+// low-order parts of two values with one packed subtraction (FADD2)
+__device__ __forceinline__ void lo_part2(uint32_t v0, uint32_t v1, uint32_t& l0, uint32_t& l1) {
+  unsigned long long x, y, d;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(x) : "r"(v0), "r"(v1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(y) : "r"(v0 & 0xffffe000u), "r"(v1 & 0xffffe000u));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  asm("mov.b64 {%0,%1}, %2;" : "=r"(l0), "=r"(l1) : "l"(d));
 }
 
 // One lane of a converged warp.  Unlike `lane == 0`, ptxas knows that code guarded by elect.sync runs

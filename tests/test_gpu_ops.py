@@ -36,6 +36,11 @@ CONV_CASES = [
     (2, 96, 14, 42, 32, 3, 1, 0, True, "elu"),       # valid conv on padded input, rows shorter than a tile
     (2, 32, 26, 82, 16, 3, 1, 0, True, "elu"),       # BN = 16
     (1, 288, 14, 22, 288, 3, 1, 0, True, "elu"),     # refine decoder, channel-padded 262 -> 288
+    # conv_tc4 (persistent variant: more tiles than SMs, several tiles per CTA, pipelines running across tiles)
+    (6, 64, 48, 80, 64, 3, 1, 1, False, "none"),     # 180 tiles, BN = 64 (two accumulator sets), 18 k-blocks
+    (5, 32, 40, 100, 128, 3, 1, 1, True, "relu"),    # 160 tiles with a ragged last tile per image, BN = 128, odd nk
+    (4, 96, 50, 100, 64, 1, 1, 0, True, "none"),     # 1x1: a chunk per k-block, 3 k-blocks per tile (group parity flips)
+    (6, 32, 30, 130, 32, 3, 1, 0, True, "elu"),      # BN = 32, valid conv: the pad-0 data gradient steps backwards
 ]
 
 
@@ -181,6 +186,8 @@ TC_CASES = [
     (1, 96, 98, 322, 32, 3, 1, 0),      # decoder upconv(1,1) on the padded input
     (1, 32, 98, 322, 16, 3, 1, 0),      # decoder upconv(0,0)
     (3, 512, 6, 20, 256, 1, 1, 0),      # pose squeeze
+    (6, 64, 48, 160, 64, 3, 1, 1),      # layer1 at the bench batch: 360 tiles, the persistent conv_tc4 path
+    (6, 128, 50, 162, 64, 3, 1, 0),     # decoder upconv(2,1): K = 1152 on one accumulator per product class
 ]
 
 
