@@ -31,20 +31,36 @@ constexpr int T4_WTMA_WARP = 13, T4_PTMA_WARP = 14, T4_MMA2_WARP = 15;
 constexpr int T4_EPI_WARP0 = 16, T4_EPIW = 4;
 constexpr int T4_NTHREADS = (T4_EPI_WARP0 + T4_EPIW) * 32;  // 640
 constexpr int PBOX4 = 64;                                   // patch rows per TMA box
+// Timing experiment (fd_debug_set_conv_trace + tools/trace_conv3.py): CTA 0 stamps clock64() into
+// trace[role][k-block over all its tiles][4] (role 0 = A splitter group 0, 1 = MMA issuers, 2 = epilogue, per tile)
+constexpr int T4_TRACE_KB = 256;
+#define T4_TRACE(role, kb, slot)                                                                   \
+  do {                                                                                             \
+    if (tracing && (kb) < T4_TRACE_KB) a.trace[((role) * T4_TRACE_KB + (kb)) * 4 + (slot)] = clock64(); \
+  } while (0)
 
 template <int BN>
 struct Cfg4 {
   static constexpr int B_TILE = BN * 128;
   static constexpr int WSTAGE = 2 * B_TILE;                             // [W ; W_lo]
   static constexpr int MAXST = 8;
-  static constexpr int MISC = 1024 /*align*/ + 512 /*barriers, zero row*/ + 1024 /*CTA channel sums*/;
+  // Output staging for the TMA stores: SBLK blocks of [128 rows x 32 columns] (SWIZZLE_128B image).  Plain
+  // st.global from the epilogue warps (32 rows x 16 B per instruction) halved the k-block rate of the main loop for
+  // as long as an epilogue ran -- the splitters' ld.shared queue behind those stores in the SM's one L1 pipe
+  // (trace with FD_TC4_EXP=1: no stores, no slow-down) -- the TMA unit reads the tile through the async proxy.
+  static constexpr int NBLK = BN / 32;
+  static constexpr int SBLK = NBLK < 2 ? NBLK : 2;
+  static constexpr int STG = SBLK * 128 * 128;
+  static constexpr int MISC = 1024 /*align*/ + STG + 512 /*barriers, zero row*/ + 1024 /*CTA channel sums*/;
   static constexpr int SMEM_MAX = 232448;
   static constexpr int TST = 2;                                         // TMEM A-ring slots: one per splitter group
   static constexpr int ACC0 = TST * 64;
   static constexpr bool PAIR = BN <= 64;
   static constexpr int NSETS = BN <= 64 ? 2 : 1;                        // accumulator sets in tensor memory
   static constexpr int NMAIN = BN <= 64 ? 1 : 2;
-  static constexpr int SETCOLS = PAIR ? BN + NMAIN * 2 * BN : (1 + NMAIN) * BN;
+  // PAIR: [main | corr] per rotation slot -- A * [W ; W_lo] lands in both halves, A_lo * W is added to the corr
+  // half (one accumulator less to read back than conv_tc3's separate corr1); else corr + NMAIN mains
+  static constexpr int SETCOLS = PAIR ? NMAIN * 2 * BN : (1 + NMAIN) * BN;
   static_assert(ACC0 + NSETS * SETCOLS <= 512, "tensor memory");
 };
 
@@ -52,10 +68,25 @@ struct Tile4 {
   int img, r0, n0, rows_valid;
 };
 
+// n / d for 0 <= n < 2^23, d > 0, inv = 1.0f / d: the per-tile set-up (tile id -> image / row, row -> (ho, wo)) sat
+// on the critical path at every tile boundary with ~1500 clk of dependent integer-division code (role trace)
+__device__ __forceinline__ int fast_div(int n, int d, float inv) {
+  int q = __float2int_rz(__int2float_rn(n) * inv);
+  const int r = n - q * d;
+  q += (r >= d) - (r < 0);
+  return q;
+}
+// bits u of [0, n) with lo <= u < hi
+__device__ __forceinline__ uint32_t range_bits(int lo, int hi, int n) {
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > n ? n : hi;
+  return hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+}
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(T4_NTHREADS, 1)
 conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
-                const int patch_rows, const int nstages, const int gx, const int total_tiles) {
+                const __grid_constant__ CUtensorMap tm_y, const int patch_rows, const int nstages, const int gx, const int total_tiles) {
   using C = Cfg4<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -64,7 +95,8 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   const uint32_t wbase = base + 2u * patch_bytes;
   auto b_raw = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE; };
   auto b_lo = [&](int s) { return wbase + (uint32_t)s * C::WSTAGE + C::B_TILE; };
-  const uint32_t bars = wbase + (uint32_t)nstages * C::WSTAGE;
+  const uint32_t stg = wbase + (uint32_t)nstages * C::WSTAGE;      // output staging (epilogue warps)
+  const uint32_t bars = stg + (uint32_t)C::STG;
   auto wland_bar = [&](int s) { return bars + 8u * s; };                        // W tile landed (TMA tx)
   auto wready_bar = [&](int s) { return bars + 8u * (C::MAXST + s); };          // W_lo written
   auto wfree_bar = [&](int s) { return bars + 8u * (2 * C::MAXST + s); };       // MMAs done with the stage
@@ -82,6 +114,8 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   auto ring_next = [&](int& st, uint32_t& ph) { if (++st == nstages) { st = 0; ph ^= 1u; } };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool ktrace = a.trace && blockIdx.x == 0;
+  if (ktrace && tid == 0) a.trace[3 * T4_TRACE_KB * 4 + 0] = clock64();
   // Tiles never cross an image (see conv_tc3.cu).  Tile id T -> (m tile x, n tile y), x fastest.
   const int HoWo = a.Ho * a.Wo;
   const int tpi = (HoWo + BM - 1) / BM;
@@ -89,10 +123,11 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   const int nchunk = a.Cg / BK;
   const int nk = taps * nchunk;
   const int span = (a.KH - 1) * a.Wg + (a.KW - 1);         // largest tap shift
+  const float inv_gx = 1.0f / (float)gx, inv_tpi = 1.0f / (float)tpi, inv_wo = 1.0f / (float)a.Wo;
   auto tile_of = [&](int T) {
     Tile4 t;
-    const int y = T / gx, x = T - y * gx;
-    t.img = x / tpi;
+    const int y = fast_div(T, gx, inv_gx), x = T - y * gx;
+    t.img = fast_div(x, tpi, inv_tpi);
     t.r0 = (x - t.img * tpi) * BM;
     t.n0 = y * BN;
     t.rows_valid = HoWo - t.r0 < BM ? HoWo - t.r0 : BM;
@@ -104,16 +139,14 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     mask = 0;
     if (row < t.rows_valid) {
       const int r = t.r0 + row;
-      const int ho = r / a.Wo, wo = r - ho * a.Wo;
+      const int ho = fast_div(r, a.Wo, inv_wo), wo = r - ho * a.Wo;
       int hq, wq;
       if (MODE == 0) {
-        hq = ho - a.pad; wq = wo - a.pad;
-        for (int u = 0; u < a.KH; ++u) mask |= (uint32_t)(hq + u >= 0 && hq + u < a.Hg) << u;
-        for (int u = 0; u < a.KW; ++u) mask |= (uint32_t)(wq + u >= 0 && wq + u < a.Wg) << (8 + u);
+        hq = ho - a.pad; wq = wo - a.pad;        // tap u reads hq + u: valid for -hq <= u < Hg - hq
+        mask = range_bits(-hq, a.Hg - hq, a.KH) | (range_bits(-wq, a.Wg - wq, a.KW) << 8);
       } else {
-        hq = ho + a.pad; wq = wo + a.pad;
-        for (int u = 0; u < a.KH; ++u) mask |= (uint32_t)(hq - u >= 0 && hq - u < a.Hg) << u;
-        for (int u = 0; u < a.KW; ++u) mask |= (uint32_t)(wq - u >= 0 && wq - u < a.Wg) << (8 + u);
+        hq = ho + a.pad; wq = wo + a.pad;        // tap u reads hq - u: valid for hq - Hg < u <= hq
+        mask = range_bits(hq - a.Hg + 1, hq + 1, a.KH) | (range_bits(wq - a.Wg + 1, wq + 1, a.KW) << 8);
       }
       lin = (t.img * a.Hg + hq) * a.Wg + wq;
       mask |= 1u << 31;
@@ -191,20 +224,22 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
     int gbase = 0, gcb = 0;                       // k-blocks / chunks of the earlier tiles
     uint32_t nuse = 0;                            // uses of this group's TMEM slot so far
+    const bool tracing = ktrace && lane == 0 && q == 0 && half == 0;
     for (int T = blockIdx.x; T < total_tiles; T += gridDim.x, gbase += nk, gcb += nchunk) {
       const Tile4 tl = tile_of(T);
       int lin;
       uint32_t vm;
       row_geom(tl, row, lin, vm);
-      const int kb0 = (half - gbase) & 1;
-      int c = kb0 / taps, kh, kw;
+      const int kb0 = (half - gbase) & 1;        // 0 or 1
+      int c = kb0 >= taps ? 1 : 0, kh, kw;
       {
         const int tap0 = kb0 - c * taps;
-        kh = tap0 / a.KW;
+        kh = tap0 >= a.KW ? 1 : 0;
         kw = tap0 - kh * a.KW;
       }
       int chunk_seen = -1, pr0 = 0;
       for (int kb = kb0; kb < nk; kb += 2, ++nuse) {
+        T4_TRACE(0, gbase + kb, 0);
         const int tap = kh * a.KW + kw;
         const int gc = gcb + c, pb = gc & 1;
         if (c != chunk_seen) {
@@ -240,10 +275,12 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
             kw = 0;
             if (++kh == a.KH) { kh = 0; ++c; }
           }
+        T4_TRACE(0, gbase + kb, 1);
         if (nuse >= 1) {
           mbar_wait(tfree_bar(half), (nuse - 1u) & 1u);
           tc_fence_after();
         }
+        T4_TRACE(0, gbase + kb, 2);
         tmem_st16(tcol, *reinterpret_cast<const uint32_t(*)[16]>(&hi[0]));
         tmem_st16(tcol + 16u, *reinterpret_cast<const uint32_t(*)[16]>(&hi[16]));
         if (!(a.flags & 0x800)) {
@@ -254,6 +291,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         tc_fence_before();
         __syncwarp();
         if (elect_one()) mbar_arrive(tfull_bar(half));
+        T4_TRACE(0, gbase + kb, 3);
       }
     }
   } else if (warp == T4_WTMA_WARP) {
@@ -318,6 +356,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     int s = 0, gbase = 0, ti = 0;
     uint32_t sph = 0, nuse = 0;
     if (me) ring_next(s, sph);
+    const bool tracing = ktrace && lane == 0;
     for (int T = blockIdx.x; T < total_tiles; T += gridDim.x, gbase += nk, ++ti) {
       const int set = ti % C::NSETS;
       const uint32_t d_corr = tmem_base + (uint32_t)(C::ACC0 + set * C::SETCOLS);
@@ -327,25 +366,28 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       }
       for (int kb = (me - gbase) & 1; kb < nk; kb += 2, ++nuse, ring_next(s, sph), ring_next(s, sph)) {
         const int g = gbase + kb;
+        T4_TRACE(1, g, 0);
         mbar_wait(wready_bar(s), sph);
+        T4_TRACE(1, g, 1);
         mbar_wait(tfull_bar(me), nuse & 1u);
         if (g > 0) mbar_wait(turn_bar(me), (uint32_t)((g - 1) >> 1) & 1u);   // the other issuer has issued g-1
         tc_fence_after();
+        T4_TRACE(1, g, 2);
         if (elect_one()) {
           const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
           const uint32_t ta = tmem_base + (uint32_t)(me * 64), tal = ta + 32u;
           if (a.flags & 0x800) {
-            const uint32_t d_main = d_corr + (uint32_t)(C::PAIR ? BN + (kb % C::NMAIN) * 2 * BN : (1 + kb % C::NMAIN) * BN);
+            const uint32_t d_main = d_corr + (uint32_t)(C::PAIR ? (kb % C::NMAIN) * 2 * BN : (1 + kb % C::NMAIN) * BN);
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k)
               umma_tf32_ts(d_main, ta + 8u * k, db + (uint64_t)(k * 32 >> 4), idesc, (kb >= C::NMAIN) || (k != 0));
           } else if (C::PAIR) {
-            const uint32_t d_pair = d_corr + (uint32_t)(BN + (kb % C::NMAIN) * 2 * BN);
+            const uint32_t d_pair = d_corr + (uint32_t)((kb % C::NMAIN) * 2 * BN);
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const uint64_t adv = (uint64_t)(k * 32 >> 4);
-              umma_tf32_ts(d_corr, tal + 8u * k, db + adv, idesc, (kb | k) != 0);
-              umma_tf32_ts(d_pair, ta + 8u * k, db + adv, idesc2, (kb >= C::NMAIN) || (k != 0));
+              umma_tf32_ts(d_pair, ta + 8u * k, db + adv, idesc2, (kb >= C::NMAIN) || (k != 0));   // [A W | A W_lo]
+              umma_tf32_ts(d_pair + (uint32_t)BN, tal + 8u * k, db + adv, idesc, 1);               // += A_lo W
             }
           } else {
             const uint32_t d_main = d_corr + (uint32_t)((1 + kb % C::NMAIN) * BN);
@@ -362,6 +404,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           umma_commit(tfree_bar(me));
         }
         __syncwarp();
+        T4_TRACE(1, g, 3);
       }
       if (elect_one()) umma_commit(accfull_bar(set));
       __syncwarp();
@@ -374,14 +417,14 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool single = (a.flags & 0x800) != 0;
     const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
-    const int nacc = single ? nmain : (C::PAIR ? 2 * nmain + 1 : nmain + 1);
+    const int nacc = single ? nmain : (C::PAIR ? 2 * nmain : nmain + 1);
     int ti = 0;
+    const bool tracing = ktrace && et == 0;
     for (int T = blockIdx.x; T < total_tiles; T += gridDim.x, ++ti) {
       const Tile4 tl = tile_of(T);
       const int set = ti % C::NSETS;
+      T4_TRACE(2, ti, 0);
       const uint32_t trow = tlane + (uint32_t)(C::ACC0 + set * C::SETCOLS);
-      const long m = (long)tl.img * HoWo + tl.r0 + row;
-      const bool row_ok = row < tl.rows_valid;
       if (a.stats) {
         for (int i = et; i < 2 * BN; i += T4_EPIW * 32)
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)i), "f"(0.f) : "memory");
@@ -389,8 +432,14 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       }
       mbar_wait(accfull_bar(set), (uint32_t)(ti / C::NSETS) & 1u);
       tc_fence_after();
+      T4_TRACE(2, ti, 1);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
+        if ((c & (32 * C::SBLK - 1)) == 0) {
+          // the staging blocks are free once the TMA unit has read the previous pass out of them
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 2, %0;" ::"n"(T4_EPIW * 32) : "memory");
+        }
         // accumulators in summation order: main, corr2 (PAIR) ..., then the A_lo * W correction
         float acc[16];
 #pragma unroll
@@ -401,9 +450,13 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           for (int u = 0; u < 2; ++u) {
             const int i = g + u;
             if (i < nacc) {
-              const int col = single ? (C::PAIR ? BN + 2 * i * BN : (1 + i) * BN)
-                                     : (i == nacc - 1 ? 0 : (C::PAIR ? BN + i * BN : (1 + i) * BN));
-              tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);
+              const int col = C::PAIR ? (single ? 2 * i * BN : i * BN)
+                                      : (single ? (1 + i) * BN : (i == nacc - 1 ? 0 : (1 + i) * BN));
+              if (!(a.flags & 0x20000)) tmem_ld16_nowait(trow + (uint32_t)(col + c), v[u]);   // timing experiment
+              else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[u][e] = 0u;
+              }
             }
           }
           tmem_wait_ld();
@@ -420,6 +473,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           tc_fence_before();
           __syncwarp();
           if (elect_one()) mbar_arrive(accfree_bar(set));
+          T4_TRACE(2, ti, 2);
         }
         if (a.stats) {
           // rows past the tile end hold exact zeros (zero A rows), so they add nothing
@@ -445,12 +499,22 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
             asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(BN + ch)), "f"(s2[0]) : "memory");
           }
         }
-        if (row_ok && tl.n0 + c < a.N) {
+        {
           float o[16];
           bias_act16(acc, a.bias ? a.bias + tl.n0 + c : nullptr, a.act, o);
-          float4* dst = reinterpret_cast<float4*>(a.y + m * a.N + tl.n0 + c);
+          stage_out16(stg, row, c & (32 * C::SBLK - 1), o);
+        }
+        if (((c + 16) & (32 * C::SBLK - 1)) == 0) {
+          // pass complete: y viewed as [image][pixel][channel], rows past the end of the image are clipped by the TMA unit
+          fence_async_proxy();
+          asm volatile("bar.sync 2, %0;" ::"n"(T4_EPIW * 32) : "memory");
+          if (et == 0 && !(a.flags & 0x10000)) {   // 0x10000: timing experiment without the stores
+            const int c0 = c + 16 - 32 * C::SBLK;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+            for (int blk = 0; blk < C::SBLK; ++blk)
+              tma_store_3d(&tm_y, stg + (uint32_t)blk * (128u * 128u), tl.n0 + c0 + 32 * blk, tl.r0, tl.img);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
       }
       if (a.stats) {
@@ -462,10 +526,13 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           if (ch < a.N) atomicAdd(a.stats + (long)stat * a.N + ch, (double)v);
         }
       }
+      T4_TRACE(2, ti, 3);
     }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last stores have left the CTA
   }
   tc_fence_before();
   __syncthreads();
+  if (ktrace && tid == 0) a.trace[3 * T4_TRACE_KB * 4 + 4] = clock64();
   if (warp == T4_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
@@ -524,8 +591,11 @@ int launch_tc4(const TcArgs& a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_map_2d(&tx, a.x, (long)a.B * a.Hg * a.Wg, a.Cg, PBOX4);
   if (rc) return rc;
+  CUtensorMap ty;
+  rc = make_map_3d(&ty, a.y, a.B, (long)a.Ho * a.Wo, a.N, BM);
+  if (rc) return rc;
   const int smem = 2 * prows * 128 + nstages * C::WSTAGE + C::MISC;
-  conv_tc4_kernel<BN, MODE><<<sms, T4_NTHREADS, smem, st>>>(a, tw, tx, prows, nstages, gx, total);
+  conv_tc4_kernel<BN, MODE><<<sms, T4_NTHREADS, smem, st>>>(a, tw, tx, ty, prows, nstages, gx, total);
   FD_CHECK_LAUNCH();
   return 0;
 }
@@ -534,8 +604,16 @@ int launch_tc4(const TcArgs& a, cudaStream_t st) {
 
 namespace fd {
 // returns -1 when this variant does not take the problem (the caller falls back to conv_tc3 / conv_tc2)
-int conv_tc4_dispatch(const TcArgs& a, int mode, cudaStream_t st) {
-  if (a.stride != 1 || a.Cg % BK != 0 || a.KH > 8 || a.KW > 8 || a.M >= (1L << 31) || a.trace) return -1;
+int conv_tc4_dispatch(const TcArgs& a0, int mode, cudaStream_t st) {
+  TcArgs a = a0;
+  a.trace = g_conv_trace_host;
+  static int exp_flags = -1;                    // FD_TC4_EXP: timing experiments (1: no output stores, 2: no TMEM reads)
+  if (exp_flags < 0) {
+    const char* e = getenv("FD_TC4_EXP");
+    exp_flags = e ? atoi(e) << 16 : 0;
+  }
+  a.flags |= exp_flags;
+  if (a.stride != 1 || a.Cg % BK != 0 || a.KH > 8 || a.KW > 8 || a.M >= (1L << 23)) return -1;   // fast_div range
   if ((long)a.B * a.Hg * a.Wg >= (1L << 31) - 65536) return -1;
   if ((((uintptr_t)a.w | (uintptr_t)a.x | (uintptr_t)a.y) & 15) != 0) return -1;
   if (a.N % 128 == 0) return mode == 0 ? launch_tc4<128, 0>(a, st) : launch_tc4<128, 1>(a, st);
