@@ -264,29 +264,6 @@ conv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_
 constexpr int BP = 32;                       // pixels (reduction elements) per stage
 constexpr int BLK = BP * 128;                // bytes of one [32 px x 32 ch] block
 
-struct WgTcArgs {
-  const float* x;   // [B,H,W,Cin]
-  float* dw;        // [N][K]
-  int B, H, W, Cin, Ho, Wo, N, KH, KW, stride, pad;
-  int M, K;
-  int p_per_split;  // pixels per blockIdx.z (multiple of BP)
-  int dbg;
-  int flags;        // bit 0: per-warp elected barrier arrivals + cp.async groups
-};
-
-// MN-major tf32 operands must use the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms: within a
-// 128-byte row the 32-byte chunk index is XORed with row & 3; 4-row groups of 512 B).  Descriptor:
-// 32-float column blocks `lbo` bytes apart, 4-row groups 512 B apart.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
-  return d;
-}
-
 template <int BN>
 struct WgCfg {
   static constexpr int NB = BN / 32;                       // dY column blocks
@@ -814,6 +791,16 @@ int fd_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H,
   a.flags = tc2_flags();
   FD_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "conv_wgrad_tc: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  // default: Xg operand in tensor memory (conv_wgrad2.cu); FD_WGRAD2=0 keeps both operands in shared memory
+  static int use_v2 = -1;
+  if (use_v2 < 0) {
+    const char* e = getenv("FD_WGRAD2");
+    use_v2 = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_v2 && !(a.flags & ~0x800)) {
+    int rc = fd::conv_wgrad2_dispatch(a, dy, st);
+    if (rc >= 0) return rc;
+  }
   if (Cout % 128 == 0) return launch_wgrad_tc<128>(a, dy, st);
   if (Cout % 64 == 0) return launch_wgrad_tc<64>(a, dy, st);
   return launch_wgrad_tc<32>(a, dy, st);

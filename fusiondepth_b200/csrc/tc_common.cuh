@@ -31,10 +31,22 @@ int conv_tc3_dispatch(const TcArgs& a, int mode, cudaStream_t st);
 // conv_tc4.cu: persistent variant of conv_tc3 (epilogue overlapped with the next tile) for launches with more
 // tiles than SMs; returns -1 when it does not take the problem
 int conv_tc4_dispatch(const TcArgs& a, int mode, cudaStream_t st);
+struct WgTcArgs {
+  const float* x;   // [B,H,W,Cin]
+  float* dw;        // [N][K]
+  int B, H, W, Cin, Ho, Wo, N, KH, KW, stride, pad;
+  int M, K;
+  int p_per_split;  // pixels per blockIdx.z (multiple of 32)
+  int dbg;
+  int flags;        // bit 0: per-warp elected barrier arrivals + cp.async groups; 0x800: single-pass TF32
+};
+// conv_wgrad2.cu: weight gradient with the gathered-input operand in tensor memory; -1 = not taken
+int conv_wgrad2_dispatch(const WgTcArgs& a, const float* dy, cudaStream_t st);
 }  // namespace fd
 
 namespace {
 using fd::TcArgs;
+using fd::WgTcArgs;
 constexpr int BM = 128, BK = 32;
 constexpr int A_TILE = BM * 128;   // bytes of one [128 rows x 32 floats] tile
 
@@ -83,6 +95,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
   d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// MN-major tf32 operands must use the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms: within a
+// 128-byte row the 32-byte chunk index is XORed with row & 3; 4-row groups of 512 B).  Descriptor:
+// 32-float column blocks `lbo` bytes apart, 4-row groups 512 B apart.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
   return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
