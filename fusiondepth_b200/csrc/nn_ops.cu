@@ -141,7 +141,7 @@ __device__ __forceinline__ void stv(float* p, const float (&v)[VEC]) {
 }
 
 struct BnGeom { int groups, gx, gy; dim3 grid, block; };
-constexpr int BN_MAX_PARTS = 96;      // partial rows of the statistic kernels (workspace: (1 + parts) * 2C doubles + counters)
+constexpr int BN_MAX_PARTS = 296;     // partial rows of the statistic kernels (workspace: (1 + parts) * 2C doubles + counters)
 
 // Last-block fold of the per-block partial sums: block (bx, by) has written its 2*VEC*nx partials to
 // part[by][...]; the last block of column bx to arrive (ticket) adds the rows in a fixed order, so the result
@@ -171,12 +171,24 @@ __device__ __forceinline__ void bn_fold_partials(double* __restrict__ ws, double
 #pragma unroll
   for (int i = 0; i < VEC; ++i) sa[i] = sb[i] = 0.0;
   if (c < C) {
-    for (unsigned r = threadIdx.y; r < gridDim.y; r += ny) {
+    // four partial rows in flight per thread (the row loop is a chain of L2 round trips otherwise: with 96 rows and
+    // 16 lanes it cost more than streaming the tensor), summed in row order
+#pragma unroll 1
+    for (unsigned r0 = threadIdx.y; r0 < gridDim.y; r0 += 4 * ny) {
+      double va[4][VEC], vb[4][VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        sa[i] += part[(long)r * 2 * C + c + i];
-        sb[i] += part[(long)r * 2 * C + C + c + i];
+      for (int j = 0; j < 4; ++j) {
+        const unsigned r = r0 + j * ny;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          va[j][i] = r < gridDim.y ? part[(long)r * 2 * C + c + i] : 0.0;
+          vb[j][i] = r < gridDim.y ? part[(long)r * 2 * C + C + c + i] : 0.0;
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { sa[i] += va[j][i]; sb[i] += vb[j][i]; }
     }
   }
 #pragma unroll
