@@ -8,6 +8,8 @@ from torch.profiler import profile, ProfilerActivity
 import bench
 from fusiondepth_b200 import _lib, synth, training
 
+if len(sys.argv) > 2:
+    bench.select_workload(sys.argv[2])          # r18 (default) / r50
 _lib.load()
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
