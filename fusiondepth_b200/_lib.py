@@ -114,6 +114,11 @@ _SIGNATURES = {
     "fd_mean_hw_fwd": (c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "fd_mean_hw_bwd": (c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "fd_adam_step": (c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P, _F, _P]),
+    "fd_lanczos_ksize": (c_int, [_I, _I]),
+    "fd_lanczos_coeffs": (c_int, [_I, _I, _P, _P]),
+    "fd_resize_lanczos_u8": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "fd_color_jitter_u8": (c_int, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "fd_image_to_tensor": (c_int, [_P, _P, _I, _I, _I, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

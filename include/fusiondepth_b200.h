@@ -316,6 +316,33 @@ int fd_mean_hw_bwd(const float* dy, float* dx, int B, int HW, int C, float scale
 int fd_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                  float beta2, float eps, int* state, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-device colour side of the data producer: datasets/mono_dataset.py:85-104
+ * (`preprocess`: pyramid of transforms.Resize(.., Image.ANTIALIAS), each scale from the previous one;
+ * ColorJitter; ToTensor) and 156-206 (flip of the native image in get_color), on uint8 HWC images in device
+ * memory, bit-identical to Pillow 12 / torchvision 0.26 `_functional_pil` (oracle/data_oracle.py).
+ *
+ * fd_lanczos_ksize / fd_lanczos_coeffs: HOST helpers.  Pillow's 22-bit fixed-point Lanczos-3 window for
+ *   resizing `in_size` samples to `out_size`: bounds[out][2] = (first input sample, count),
+ *   kk[out][ksize] int32 weights (zero padded).  The caller uploads them once per size pair.
+ * fd_resize_lanczos_u8: src [B,Hin,Win,3] -> dst [B,Hout,Wout,3]; horizontal pass first into
+ *   tmp [B,Hin,Wout,3] (uint8 intermediate, as PIL), then vertical.  flip [B] uint8 or NULL: image b is
+ *   mirrored left-right before the resize.
+ * fd_color_jitter_u8: torchvision ColorJitter in place with explicit parameters: order [B,4] = the
+ *   permutation of (0 brightness, 1 contrast, 2 saturation, 3 hue) drawn for image b, factors [B,4]
+ *   indexed by op: blend factors for ops 0-2, for hue the uint8 shift int32(hue * 255) & 255 as a float;
+ *   NaN = op skipped.  lum_sums: B x uint64 workspace.
+ * fd_image_to_tensor: [B,H,W,3] uint8 -> [B,3,H,W] float32 = u8 / 255 (transforms.ToTensor). */
+int fd_lanczos_ksize(int in_size, int out_size);
+int fd_lanczos_coeffs(int in_size, int out_size, int* bounds_host, int* kk_host);
+int fd_resize_lanczos_u8(const unsigned char* src, unsigned char* tmp, unsigned char* dst, int B, int Hin,
+                         int Win, int Hout, int Wout, const int* bounds_w, const int* kk_w, int ksize_w,
+                         const int* bounds_h, const int* kk_h, int ksize_h, const unsigned char* flip,
+                         void* stream);
+int fd_color_jitter_u8(unsigned char* img, int B, int H, int W, const int* order, const float* factors,
+                       unsigned long long* lum_sums, void* stream);
+int fd_image_to_tensor(const unsigned char* img, float* out, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
