@@ -25,11 +25,9 @@
 
 namespace {
 
-constexpr int T4_WSPLITW = 4, T4_ASPLITW = 8;
-constexpr int T4_MMA_WARP = T4_WSPLITW + T4_ASPLITW;        // 12
-constexpr int T4_WTMA_WARP = 13, T4_PTMA_WARP = 14, T4_MMA2_WARP = 15;
-constexpr int T4_EPI_WARP0 = 16, T4_EPIW = 4;
-constexpr int T4_NTHREADS = (T4_EPI_WARP0 + T4_EPIW) * 32;  // 640
+constexpr int T4_WSPLITW = 4, T4_EPIW = 4;
+// warp layout for NG splitter groups: [0,4) W_lo splitters, [4, 4+4NG) A splitters, then MMA issuer 0, W TMA,
+// patch TMA, MMA issuer 1, four epilogue warps (warp index % 4 = TMEM lane quadrant for splitters and epilogue)
 constexpr int PBOX4 = 64;                                   // patch rows per TMA box
 // Timing experiment (fd_debug_set_conv_trace + tools/trace_conv3.py): CTA 0 stamps clock64() into
 // trace[role][k-block over all its tiles][4] (role 0 = A splitter group 0, 1 = MMA issuers, 2 = epilogue, per tile)
@@ -53,7 +51,16 @@ struct Cfg4 {
   static constexpr int STG = SBLK * 128 * 128;
   static constexpr int MISC = 1024 /*align*/ + STG + 512 /*barriers, zero row*/ + 1024 /*CTA channel sums*/;
   static constexpr int SMEM_MAX = 232448;
-  static constexpr int TST = 2;                                         // TMEM A-ring slots: one per splitter group
+  // A splitter groups = TMEM A-ring slots.  Measured: a third group (NG = 3 for BN <= 64, 768 threads at 80
+  // registers) leaves the 64-wide kernel at ~570-590 clk per k-block -- it is not splitter-bound but at its
+  // shared-memory roofline: per k-block the MMAs read 24 KB of B, TMA writes 6.4 KB of patch + 8 KB of W, the
+  // splitters read 16 KB and the W_lo pass reads + writes 16 KB = 70 KB through a 128 B/clk port = 550 clk.
+  static constexpr int NG = 2;
+  static constexpr int TST = NG;
+  static constexpr int ASPLITW = 4 * NG;
+  static constexpr int MMA_WARP = T4_WSPLITW + ASPLITW, WTMA_WARP = MMA_WARP + 1, PTMA_WARP = MMA_WARP + 2,
+                       MMA2_WARP = MMA_WARP + 3, EPI_WARP0 = MMA_WARP + 4;
+  static constexpr int NTHREADS = (EPI_WARP0 + T4_EPIW) * 32;           // 768 / 640
   static constexpr int ACC0 = TST * 64;
   static constexpr bool PAIR = BN <= 64;
   static constexpr int NSETS = BN <= 64 ? 2 : 1;                        // accumulator sets in tensor memory
@@ -84,7 +91,7 @@ __device__ __forceinline__ uint32_t range_bits(int lo, int hi, int n) {
 }
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(T4_NTHREADS, 1)
+__global__ void __launch_bounds__(Cfg4<BN>::NTHREADS, 1)
 conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_y, const int patch_rows, const int nstages, const int gx, const int total_tiles) {
   using C = Cfg4<BN>;
@@ -101,14 +108,14 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   auto wready_bar = [&](int s) { return bars + 8u * (C::MAXST + s); };          // W_lo written
   auto wfree_bar = [&](int s) { return bars + 8u * (2 * C::MAXST + s); };       // MMAs done with the stage
   auto tfull_bar = [&](int t) { return bars + 8u * (24 + t); };                 // A / A_lo of a k-block in TMEM
-  auto tfree_bar = [&](int t) { return bars + 8u * (26 + t); };
-  auto pfull_bar = [&](int b) { return bars + 8u * (28 + b); };                 // patch buffer landed
-  auto pfree_bar = [&](int b) { return bars + 8u * (30 + b); };
-  auto accfull_bar = [&](int s) { return bars + 8u * (32 + s); };               // a tile's MMAs are complete
-  auto accfree_bar = [&](int s) { return bars + 8u * (34 + s); };               // the epilogue has read the set
-  auto turn_bar = [&](int i) { return bars + 8u * (36 + i); };                  // issuer i may issue
-  const uint32_t tmem_slot = bars + 8u * 38;
-  const uint32_t pinfo = bars + 8u * 39;                    // [2] patch start (pixel index) of the chunk in buffer b
+  auto tfree_bar = [&](int t) { return bars + 8u * (28 + t); };
+  auto pfull_bar = [&](int b) { return bars + 8u * (32 + b); };                 // patch buffer landed
+  auto pfree_bar = [&](int b) { return bars + 8u * (34 + b); };
+  auto accfull_bar = [&](int s) { return bars + 8u * (36 + s); };               // a tile's MMAs are complete
+  auto accfree_bar = [&](int s) { return bars + 8u * (38 + s); };               // the epilogue has read the set
+  auto turn_bar = [&](int i) { return bars + 8u * (40 + i); };                  // issuer i may issue
+  const uint32_t tmem_slot = bars + 8u * 42;
+  const uint32_t pinfo = bars + 8u * 43;                    // [2] patch start (pixel index) of the chunk in buffer b
   const uint32_t zero_row = bars + 384u;                    // 128 B of zeros: the "row" a padding tap reads
   const uint32_t cta_sums = bars + 512u;                    // [2][BN] floats, only with a.stats
   auto ring_next = [&](int& st, uint32_t& ph) { if (++st == nstages) { st = 0; ph ^= 1u; } };
@@ -123,6 +130,10 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   const int nchunk = a.Cg / BK;
   const int nk = taps * nchunk;
   const int span = (a.KH - 1) * a.Wg + (a.KW - 1);         // largest tap shift
+  // Active splitter groups.  A group must wait on EVERY phase of a patch-buffer barrier it uses (mbarrier parity
+  // waits only tell adjacent phases apart), i.e. touch every chunk: true when a chunk spans >= NG k-blocks; a 1x1
+  // conv (one k-block per chunk) runs on two groups, where group = chunk parity = buffer.
+  const int ng = taps >= C::NG ? C::NG : 2;
   const float inv_gx = 1.0f / (float)gx, inv_tpi = 1.0f / (float)tpi, inv_wo = 1.0f / (float)a.Wo;
   auto tile_of = [&](int T) {
     Tile4 t;
@@ -162,12 +173,12 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       mbar_init(wfree_bar(s), 1);
     }
     for (int t = 0; t < C::TST; ++t) {
-      mbar_init(tfull_bar(t), T4_ASPLITW / 2);
+      mbar_init(tfull_bar(t), 4);
       mbar_init(tfree_bar(t), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(pfull_bar(b), 1);
-      mbar_init(pfree_bar(b), taps == 1 ? T4_ASPLITW / 2 : T4_ASPLITW);   // 1x1: a chunk belongs to one group
+      mbar_init(pfree_bar(b), 4 * (taps < ng ? taps : ng));             // the groups that touch a chunk (1x1: one)
       mbar_init(accfull_bar(b), 2);                                        // both MMA issuers commit to it
       mbar_init(accfree_bar(b), T4_EPIW);
       mbar_init(turn_bar(b), 1);
@@ -176,7 +187,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
   }
-  if (warp == T4_MMA_WARP) {
+  if (warp == C::MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -215,8 +226,8 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         if (elect_one()) mbar_arrive(wready_bar(s));
       }
     }
-  } else if (warp < T4_MMA_WARP) {
-    // ======================= A splitters: group `half` takes the k-blocks g with g % 2 == half =======================
+  } else if (warp < C::MMA_WARP) {
+    // ======================= A splitters: group `half` takes the k-blocks g with g % NG == half =======================
     // (g counts k-blocks over all of this CTA's tiles; TMEM slot = half)
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int half = (warp - T4_WSPLITW) >> 2;
@@ -230,15 +241,16 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       int lin;
       uint32_t vm;
       row_geom(tl, row, lin, vm);
-      const int kb0 = (half - gbase) & 1;        // 0 or 1
-      int c = kb0 >= taps ? 1 : 0, kh, kw;
-      {
-        const int tap0 = kb0 - c * taps;
-        kh = tap0 >= a.KW ? 1 : 0;
-        kw = tap0 - kh * a.KW;
-      }
+      if (half >= ng) break;
+      const int kb0 = (half + ng - gbase % ng) % ng;                  // first k-block of the tile with g % ng == half
+      int c = 0, kh = 0, kw = 0;
+      for (int i = 0; i < kb0; ++i)
+        if (++kw == a.KW) {
+          kw = 0;
+          if (++kh == a.KH) { kh = 0; ++c; }
+        }
       int chunk_seen = -1, pr0 = 0;
-      for (int kb = kb0; kb < nk; kb += 2, ++nuse) {
+      for (int kb = kb0; kb < nk; kb += ng, ++nuse) {
         T4_TRACE(0, gbase + kb, 0);
         const int tap = kh * a.KW + kw;
         const int gc = gcb + c, pb = gc & 1;
@@ -268,9 +280,8 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         for (int e = 0; e < 32; e += 2) lo_part2(hi[e], hi[e + 1], lo[e], lo[e + 1]);
         __syncwarp();
         // last k-block of this chunk for this warp: its reads of the patch are complete
-        if (tap + 2 >= taps && elect_one()) mbar_arrive(pfree_bar(pb));
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
+        if (tap + ng >= taps && elect_one()) mbar_arrive(pfree_bar(pb));
+        for (int i = 0; i < ng; ++i)
           if (++kw == a.KW) {
             kw = 0;
             if (++kh == a.KH) { kh = 0; ++c; }
@@ -294,7 +305,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         T4_TRACE(0, gbase + kb, 3);
       }
     }
-  } else if (warp == T4_WTMA_WARP) {
+  } else if (warp == C::WTMA_WARP) {
     // ======================= W tiles by TMA =======================
     int s = 0, g = 0;
     uint32_t sph = 0;
@@ -311,7 +322,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         if (++tap == taps) { tap = 0; ++c; }
       }
     }
-  } else if (warp == T4_PTMA_WARP) {
+  } else if (warp == C::PTMA_WARP) {
     // ======================= patches by TMA: chunk gc -> buffer gc & 1 =======================
     int gc = 0;
     for (int T = blockIdx.x; T < total_tiles; T += gridDim.x) {
@@ -346,15 +357,15 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         __syncwarp();
       }
     }
-  } else if (warp == T4_MMA_WARP || warp == T4_MMA2_WARP) {
-    // ======================= MMA issuers: issuer `me` takes the k-blocks g with g % 2 == me =======================
+  } else if (warp == C::MMA_WARP || warp == C::MMA2_WARP) {
+    // ======================= MMA issuers: issuer `me` takes the k-blocks g with g % 2 == me (TMEM slot g % NG) =======================
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) |
                             ((uint32_t)(BM >> 4) << 24);                    // N = 2*BN: [W ; W_lo]
-    const int me = warp == T4_MMA_WARP ? 0 : 1;
+    const int me = warp == C::MMA_WARP ? 0 : 1;
     int s = 0, gbase = 0, ti = 0;
-    uint32_t sph = 0, nuse = 0;
+    uint32_t sph = 0;
     if (me) ring_next(s, sph);
     const bool tracing = ktrace && lane == 0;
     for (int T = blockIdx.x; T < total_tiles; T += gridDim.x, gbase += nk, ++ti) {
@@ -364,18 +375,20 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         mbar_wait(accfree_bar(set), (uint32_t)(ti / C::NSETS - 1) & 1u);
         tc_fence_after();
       }
-      for (int kb = (me - gbase) & 1; kb < nk; kb += 2, ++nuse, ring_next(s, sph), ring_next(s, sph)) {
+      for (int kb = (me - gbase) & 1; kb < nk; kb += 2, ring_next(s, sph), ring_next(s, sph)) {
         const int g = gbase + kb;
+        const int slot = g % ng;
+        const uint32_t nuse = (uint32_t)(g / ng);
         T4_TRACE(1, g, 0);
         mbar_wait(wready_bar(s), sph);
         T4_TRACE(1, g, 1);
-        mbar_wait(tfull_bar(me), nuse & 1u);
+        mbar_wait(tfull_bar(slot), nuse & 1u);
         if (g > 0) mbar_wait(turn_bar(me), (uint32_t)((g - 1) >> 1) & 1u);   // the other issuer has issued g-1
         tc_fence_after();
         T4_TRACE(1, g, 2);
         if (elect_one()) {
           const uint64_t db = make_desc(b_raw(s)), dbl = make_desc(b_lo(s));
-          const uint32_t ta = tmem_base + (uint32_t)(me * 64), tal = ta + 32u;
+          const uint32_t ta = tmem_base + (uint32_t)(slot * 64), tal = ta + 32u;
           if (a.flags & 0x800) {
             const uint32_t d_main = d_corr + (uint32_t)(C::PAIR ? (kb % C::NMAIN) * 2 * BN : (1 + kb % C::NMAIN) * BN);
 #pragma unroll
@@ -401,7 +414,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           }
           mbar_arrive(turn_bar(me ^ 1));
           umma_commit(wfree_bar(s));
-          umma_commit(tfree_bar(me));
+          umma_commit(tfree_bar(slot));
         }
         __syncwarp();
         T4_TRACE(1, g, 3);
@@ -413,7 +426,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     // ======================= epilogue: warp q owns tile rows 32q .. 32q+31, all BN columns =======================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int et = tid - T4_EPI_WARP0 * 32;          // 0..127
+    const int et = tid - C::EPI_WARP0 * 32;          // 0..127
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool single = (a.flags & 0x800) != 0;
     const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
@@ -533,7 +546,7 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   tc_fence_before();
   __syncthreads();
   if (ktrace && tid == 0) a.trace[3 * T4_TRACE_KB * 4 + 4] = clock64();
-  if (warp == T4_MMA_WARP) {
+  if (warp == C::MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
@@ -595,7 +608,7 @@ int launch_tc4(const TcArgs& a, cudaStream_t st) {
   rc = make_map_3d(&ty, a.y, a.B, (long)a.Ho * a.Wo, a.N, BM);
   if (rc) return rc;
   const int smem = 2 * prows * 128 + nstages * C::WSTAGE + C::MISC;
-  conv_tc4_kernel<BN, MODE><<<sms, T4_NTHREADS, smem, st>>>(a, tw, tx, ty, prows, nstages, gx, total);
+  conv_tc4_kernel<BN, MODE><<<sms, C::NTHREADS, smem, st>>>(a, tw, tx, ty, prows, nstages, gx, total);
   FD_CHECK_LAUNCH();
   return 0;
 }
