@@ -648,6 +648,8 @@ static int tc2_flags() {
     // GPU, cudnn.allow_tf32=True); default 3xTF32 = fp32-level accuracy, which the parity tests require.
     const char* p = getenv("FD_CONV_PRECISION");
     if (p && p[0] == 't' && p[1] == 'f') v |= 0x800;
+    const char* f = getenv("FD_TC_FENCE");
+    if (f && f[0] == '1') v |= 0x1000;
   }
   return v;
 }
@@ -678,7 +680,7 @@ static bool tc_use_v4() {
 }
 // conv_tc4 (persistent patch variant) for many-tile launches, conv_tc3 (patch variant) where it applies, else conv_tc2
 static int tc_v2_or_v3(const TcArgs& a, int mode, cudaStream_t st) {
-  if (tc_use_v3() && !(a.flags & ~0x800)) {
+  if (tc_use_v3() && !(a.flags & ~0x1800)) {
     if (tc_use_v4()) {
       int rc = fd::conv_tc4_dispatch(a, mode, st);
       if (rc >= 0) return rc;
@@ -797,7 +799,7 @@ int fd_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H,
     const char* e = getenv("FD_WGRAD2");
     use_v2 = (e && e[0] == '0') ? 0 : 1;
   }
-  if (use_v2 && !(a.flags & ~0x800)) {
+  if (use_v2 && !(a.flags & ~0x1800)) {
     int rc = fd::conv_wgrad2_dispatch(a, dy, st);
     if (rc >= 0) return rc;
   }

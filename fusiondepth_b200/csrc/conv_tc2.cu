@@ -431,6 +431,7 @@ conv_tc2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
             if (!(a.flags & 16)) umma_tf32_ts(d_main, ta + 8u * k, db + adv, idesc, (kb >= C::NMAIN) || (k != 0));
           }
         }
+        if (a.flags & 0x1000) tc_fence_before();      // FD_TC_FENCE=1: ordering experiment
         mbar_arrive(turn_bar(me ^ 1));
         if (plain) {
           mbar_arrive(sfree_bar(s));

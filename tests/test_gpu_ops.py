@@ -51,12 +51,16 @@ def test_conv2d_fwd_bwd(cuda, case):
     x = _rand((B, Cin, H, W), 1)
     w = _rand((Cout, Cin, k, k), 2, (2.0 / (Cin * k * k)) ** 0.5)
     b = _rand((Cout,), 3, 0.1) if bias else None
-    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
-    br = b.clone().requires_grad_(True) if bias else None
+    # Reference in float64 on the CPU: the fp32 CPU convolution is not a fixed oracle -- oneDNN picks its algorithm
+    # at run time, and roughly one run in ten of this file it answered the 3x3 / 48-channel case with ~5e-5 of error
+    # (18 repetitions on a B200 box: 2 failures, always that case, always on the CPU side; the CUDA output was
+    # bit-identical over 3000 launches, tools/flaky_case10.py).
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True) if bias else None
     y = F.conv2d(xr, wr, br, s, p)
     y = {"none": lambda t: t, "relu": F.relu, "elu": F.elu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](y)
     gy = _rand(tuple(y.shape), 4)
-    y.backward(gy)
+    y.backward(gy.double())
     xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
     wc = w.cuda().contiguous(memory_format=CL).requires_grad_(True)
     bc = b.cuda().requires_grad_(True) if bias else None
