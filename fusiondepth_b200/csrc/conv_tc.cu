@@ -737,7 +737,7 @@ int fd_conv2d_fwd_tc_stats(const float* x, const float* w, const float* w_lo, co
              "fd_conv2d_fwd_tc: needs Cin %% 32 == 0 and Cout %% 16 == 0 (got %d, %d)", Cin, Cout);
   FD_REQUIRE(stats == nullptr || (tc_use_v2() && bias == nullptr && act == FD_ACT_NONE),
              "fd_conv2d_fwd_tc_stats: channel statistics need the conv_tc2 kernels, no bias and no activation");
-  TcArgs a;
+  TcArgs a{};
   a.trace = nullptr;
   a.stats = stats;
   a.x = x; a.w = w; a.wlo = w_lo; a.bias = bias; a.y = y;
@@ -756,7 +756,7 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
                        int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream) {
   FD_REQUIRE(fd_conv2d_tc_supported(Cout, Cin),
              "fd_conv2d_dgrad_tc: needs Cout %% 32 == 0 and Cin %% 16 == 0 (got %d, %d)", Cout, Cin);
-  TcArgs a;
+  TcArgs a{};
   a.trace = nullptr;
   a.stats = nullptr;
   a.x = dy; a.w = wt; a.wlo = wt_lo; a.bias = nullptr; a.y = dx;
@@ -769,6 +769,19 @@ int fd_conv2d_dgrad_tc(const float* dy, const float* wt, const float* wt_lo, flo
   a.M = (long)B * H * W;
   a.K = KH * KW * Cout;
   a.flags = tc2_flags();
+  if (tc_use_v2() && tc_use_v3() && stride == 2 && !(a.flags & ~0x1800)) {
+    // the stride-2 data gradient reads 1, 2, 2 or 4 of the 9 taps depending on the output pixel's parity: four
+    // stride-1 convolutions over dY instead of one that multiplies 3/4 zeros
+    static int use_s2 = -1;
+    if (use_s2 < 0) {
+      const char* e = getenv("FD_DGRAD_S2");
+      use_s2 = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_s2) {
+      int rc = fd::conv_tc3_dgrad_s2(a, (cudaStream_t)stream);
+      if (rc >= 0) return rc;
+    }
+  }
   if (tc_use_v2()) return tc_v2_or_v3(a, 1, (cudaStream_t)stream);
   return dispatch_tc<1>(a, (cudaStream_t)stream);
 }

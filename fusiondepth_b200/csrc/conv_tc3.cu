@@ -30,6 +30,8 @@
 //   warp 14     patches by TMA     one 32-channel chunk per buffer, a whole chunk ahead
 //
 // k-block order: chunk-major (c0 outer, taps inner), W tile column = tap*Cg + c0.
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -102,10 +104,22 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   const long m0 = (long)img * HoWo + r0;
   const int rows_valid = HoWo - r0 < BM ? HoWo - r0 : BM;
   const int n0 = blockIdx.y * BN;
-  const int taps = a.KH * a.KW;
   const int nchunk = a.Cg / BK;
+  // MODE 2 (tap table): the class of this CTA (blockIdx.z), shift of its tap t
+  TcArgs::TapClass tc = a.cl[0];
+  int tsh[4] = {0, 0, 0, 0};
+  if (MODE == 2) {
+    if (blockIdx.z == 1) tc = a.cl[1];
+    if (blockIdx.z == 2) tc = a.cl[2];
+    if (blockIdx.z == 3) tc = a.cl[3];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) tsh[t] = t < tc.ntap ? tc.dh[t] * a.Wg + tc.dw[t] : 0;
+  }
+  const int taps = MODE == 2 ? tc.ntap : a.KH * a.KW;
+  const int KWt = MODE == 2 ? tc.ntap : a.KW;               // taps per kernel row (MODE 2: one row of ntap taps)
   const int nk = taps * nchunk;
-  const int span = (a.KH - 1) * a.Wg + (a.KW - 1);        // largest tap shift
+  const int span = MODE == 2 ? max(max(tsh[0], tsh[1]), max(tsh[2], tsh[3]))
+                             : (a.KH - 1) * a.Wg + (a.KW - 1);        // largest tap shift
   const bool ktrace = a.trace && blockIdx.x == 0 && blockIdx.y == 0;
   if (ktrace && tid == T3_WSPLITW * 32) a.trace[3 * T3_TRACE_KB * 4 + 0] = clock64();
 
@@ -126,7 +140,13 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       const int r = r0 + tid;
       const int ho = r / a.Wo, wo = r - ho * a.Wo;
       int hq, wq;
-      if (MODE == 0) {
+      if (MODE == 2) {
+        hq = ho; wq = wo;
+        mask = 1u;                                          // "kh = 0" is always valid; bit 8 + t = tap t is inside dY
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          mask |= (uint32_t)(t < tc.ntap && ho + tc.dh[t] < a.Hg && wo + tc.dw[t] < a.Wg) << (8 + t);
+      } else if (MODE == 0) {
         hq = ho - a.pad; wq = wo - a.pad;
         for (int t = 0; t < a.KH; ++t) mask |= (uint32_t)(hq + t >= 0 && hq + t < a.Hg) << t;
         for (int t = 0; t < a.KW; ++t) mask |= (uint32_t)(wq + t >= 0 && wq + t < a.Wg) << (8 + t);
@@ -194,7 +214,7 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     lin_max = max(lin_max, w);
   }
   // the patch: pixels [pstart, pstart + prows) of the gathered tensor
-  const int pstart = MODE == 0 ? lin_min : lin_min - span;
+  const int pstart = MODE != 1 ? lin_min : lin_min - span;
   const int prows = lin_max - lin_min + span + 1;
 
   if (warp < T3_WSPLITW) {
@@ -237,7 +257,7 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lin) : "r"(tab_lin + 4u * (uint32_t)row));
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vm) : "r"(tab_mask + 4u * (uint32_t)row));
     // patch row of this tile row's tap (0,0); rows past the image stay inside the buffer and are masked to zero
-    const int pr0 = (vm >> 31) ? lin - pstart : (MODE == 0 ? 0 : span);
+    const int pr0 = (vm >> 31) ? lin - pstart : (MODE != 1 ? 0 : span);
     int chunk_seen = -1;
     const bool tracing = ktrace && lane == 0 && q == 0 && half == 0;
     const int trole = 0;
@@ -247,19 +267,19 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     int c = half / taps, kh, kw;
     {
       const int tap0 = half - c * taps;
-      kh = tap0 / a.KW;
-      kw = tap0 - kh * a.KW;
+      kh = tap0 / KWt;
+      kw = tap0 - kh * KWt;
     }
     for (int kb = half; kb < nk; kb += 2) {
       T3_TRACE(trole, kb, 0);
-      const int tap = kh * a.KW + kw;
+      const int tap = kh * KWt + kw;
       const int t = kb % C::TST, pb = c & 1;
       if (c != chunk_seen) {
         mbar_wait(pfull_bar(pb), (c >> 1) & 1);
         chunk_seen = c;
       }
-      const int sh = kh * a.Wg + kw;
-      const uint32_t pr = (uint32_t)(MODE == 0 ? pr0 + sh : pr0 - sh);
+      const int sh = MODE == 2 ? (kw == 0 ? tsh[0] : (kw == 1 ? tsh[1] : (kw == 2 ? tsh[2] : tsh[3]))) : kh * a.Wg + kw;
+      const uint32_t pr = (uint32_t)(MODE != 1 ? pr0 + sh : pr0 - sh);
       const bool ok = ((vm >> kh) & (vm >> (8 + kw)) & 1u) != 0;
       uint32_t hi[32], lo[32];
       // padding taps read a row of zeros instead of being masked element by element
@@ -278,9 +298,9 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       if (tap + 2 >= taps && elect_one()) mbar_arrive(pfree_bar(pb));
 #pragma unroll
       for (int i = 0; i < 2; ++i)
-        if (++kw == a.KW) {
+        if (++kw == KWt) {
           kw = 0;
-          if (++kh == a.KH) { kh = 0; ++c; }
+          if (MODE == 2 || ++kh == a.KH) { kh = 0; ++c; }
         }
       T3_TRACE(trole, kb, 1);
       if (kb >= C::TST) {
@@ -305,8 +325,13 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     if (ktrace && tid == T3_WSPLITW * 32) a.trace[3 * T3_TRACE_KB * 4 + 2] = clock64();
-    const long m = m0 + row;
+    long m = m0 + row;
     const bool row_ok = row < rows_valid;
+    if (MODE == 2) {                                         // class pixel (ho, wo) -> (2 ho + oph, 2 wo + opw) of y
+      const int r = r0 + row;
+      const int ho = r / a.Wo, wo = r - ho * a.Wo;
+      m = ((long)img * a.OH + 2 * ho + tc.oph) * a.OW + 2 * wo + tc.opw;
+    }
     const uint32_t trow = tlane + (uint32_t)C::ACC0;
     const int nmain = nk < C::NMAIN ? nk : C::NMAIN;
 #pragma unroll 1
@@ -359,7 +384,7 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
           asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(cta_sums + 4u * (uint32_t)(BN + ch)), "f"(s2[0]) : "memory");
         }
       }
-      if (BN >= 32) {
+      if (BN >= 32 && MODE != 2) {
         // staged in shared memory (both patch buffers are consumed by now) and written by TMA: see conv_tc2.cu
         float o[16];
         bias_act16(acc, a.bias ? a.bias + n0 + c : nullptr, a.act, o);
@@ -372,7 +397,7 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
         for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
       }
     }
-    if (BN >= 32) {
+    if (BN >= 32 && MODE != 2) {
       fence_async_proxy();
       asm volatile("bar.sync 2, %0;" ::"n"(T3_ASPLITW * 32) : "memory");
       if (warp == T3_WSPLITW && elect_one()) {
@@ -405,8 +430,9 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
       T3_TRACE(2, kb, 1);
       if (elect_one()) {
         const int c = kb / taps, tap = kb - c * taps;
+        const int wtap = MODE == 2 ? (tap == 0 ? tc.wt[0] : (tap == 1 ? tc.wt[1] : (tap == 2 ? tc.wt[2] : tc.wt[3]))) : tap;
         mbar_expect_tx(wland_bar(s), C::B_TILE);
-        tma_load_2d(b_raw(s), &tm_w, tap * a.Cg + c * BK, n0, wland_bar(s));
+        tma_load_2d(b_raw(s), &tm_w, wtap * a.Cg + c * BK, n0, wland_bar(s));
       }
       __syncwarp();
     }
@@ -495,7 +521,13 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
 int patch_rows_needed(const TcArgs& a) {
   const long dW = a.Wg > a.Wo ? a.Wg - a.Wo : a.Wo - a.Wg;
   const long row_changes = (BM - 2) / a.Wo + 1;
-  const long need = (BM - 1) + dW * row_changes + (long)(a.KH - 1) * a.Wg + a.KW;
+  long span1 = (long)(a.KH - 1) * a.Wg + a.KW;             // largest tap shift + 1
+  if (a.ncls > 0) {
+    span1 = 1;
+    for (int i = 0; i < a.ncls; ++i)
+      for (int t = 0; t < a.cl[i].ntap; ++t) span1 = std::max(span1, (long)a.cl[i].dh[t] * a.Wg + a.cl[i].dw[t] + 1);
+  }
+  const long need = (BM - 1) + dW * row_changes + span1;
   const long rows = (need + PBOX - 1) / PBOX * PBOX;
   return rows > 4096 ? -1 : (int)rows;
 }
@@ -530,11 +562,11 @@ int launch_tc3(const TcArgs& a, cudaStream_t st) {
   rc = make_map_2d(&tx, a.x, (long)a.B * a.Hg * a.Wg, a.Cg, PBOX);
   if (rc) return rc;
   CUtensorMap ty = tw;
-  if (BN >= 32) {
+  if (BN >= 32 && MODE != 2) {
     rc = make_map_3d(&ty, a.y, a.B, (long)a.Ho * a.Wo, a.N, BM);
     if (rc) return rc;
   }
-  dim3 grid(a.B * fd::cdiv((long)a.Ho * a.Wo, BM), fd::cdiv(a.N, BN));
+  dim3 grid(a.B * fd::cdiv((long)a.Ho * a.Wo, BM), fd::cdiv(a.N, BN), MODE == 2 ? a.ncls : 1);
   conv_tc3_kernel<BN, MODE><<<grid, T3_NTHREADS, smem, st>>>(a, tw, tx, ty, prows, nstages);
   FD_CHECK_LAUNCH();
   return 0;
@@ -547,9 +579,57 @@ bool patch_fits(const TcArgs& a) {
   return prows > 0 && stages_for<BN>(prows) >= 3;
 }
 
+template <int BN>
+int launch_tc3_tap(const TcArgs& a, cudaStream_t st) {
+  if (!patch_fits<BN>(a)) return -1;
+  return launch_tc3<BN, 2>(a, st);
+}
+
 }  // namespace
 
 namespace fd {
+int conv_tc3_dgrad_s2(const TcArgs& g, cudaStream_t st) {
+  // g: x = dY [B,Hg,Wg,Cg = Cout], w = W^T [N = Cin][KH*KW*Cout], y = dX [B,Ho,Wo,N], stride 2
+  const int H = g.Ho, W = g.Wo;
+  const bool k3 = g.KH == 3 && g.KW == 3 && g.pad == 1, k1 = g.KH == 1 && g.KW == 1 && g.pad == 0;
+  if (g.stride != 2 || !(k3 || k1) || (H & 1) || (W & 1) || g.Cg % BK != 0 || g.N % 16 != 0) return -1;
+  if (g.Hg != H / 2 || g.Wg != W / 2) return -1;
+  if ((long)g.B * g.Hg * g.Wg >= (1L << 31) - 65536 || g.M >= (1L << 31)) return -1;
+  if ((((uintptr_t)g.w | (uintptr_t)g.x | (uintptr_t)g.y) & 15) != 0) return -1;
+  const int bn = g.N % 128 == 0 ? 128 : (g.N % 64 == 0 ? 64 : (g.N % 32 == 0 ? 32 : 16));
+  TcArgs a = g;
+  a.trace = nullptr;
+  a.ncls = 0;
+  bool empty_class = false;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      TcArgs::TapClass c{};
+      for (int kh = 0; kh < g.KH; ++kh)
+        for (int kw = 0; kw < g.KW; ++kw) {
+          const int th = ph + g.pad - kh, tw = pw + g.pad - kw;        // dY row = (h + pad - kh) / 2 for h = 2 i + ph
+          if (th < 0 || tw < 0 || (th & 1) || (tw & 1)) continue;
+          c.dh[c.ntap] = th / 2; c.dw[c.ntap] = tw / 2; c.wt[c.ntap] = kh * g.KW + kw;
+          ++c.ntap;
+        }
+      if (c.ntap == 0) { empty_class = true; continue; }
+      c.oph = ph; c.opw = pw;
+      a.cl[a.ncls++] = c;
+    }
+  // the classes run as blockIdx.z of ONE launch (four launches of 24 ... 90 CTAs each ran one after the other)
+  a.KH = 1; a.KW = 4; a.stride = 1; a.pad = 0;
+  a.OH = H; a.OW = W;
+  a.Ho = H / 2; a.Wo = W / 2;
+  a.M = (long)g.B * a.Ho * a.Wo;
+  if (empty_class) {                             // 1x1 / 2: only the even-even pixels receive a gradient
+    cudaError_t e = cudaMemsetAsync(g.y, 0, sizeof(float) * (size_t)g.B * H * W * g.N, st);
+    if (e != cudaSuccess) { fd::set_error("conv_tc3_dgrad_s2: memset failed: %s", cudaGetErrorString(e)); return 1; }
+  }
+  const int rc = bn == 128 ? launch_tc3_tap<128>(a, st)
+                           : (bn == 64 ? launch_tc3_tap<64>(a, st)
+                                       : (bn == 32 ? launch_tc3_tap<32>(a, st) : launch_tc3_tap<16>(a, st)));
+  return rc;
+}
+
 // returns -1 when this variant does not take the problem (the caller falls back to conv_tc2)
 int conv_tc3_dispatch(const TcArgs& a0, int mode, cudaStream_t st) {
   TcArgs a = a0;

@@ -20,6 +20,12 @@ struct TcArgs {
   int flags;          // conv_tc2: bit 0 = loader signals `landed` per warp through cp.async groups
   double* stats;      // conv_tc2 forward, optional: [2][N] per-channel sum / sum of squares of y (+=)
   long long* trace;   // timing experiment (fd_debug_set_conv_trace): clock64() stamps of CTA (0,0), else null
+  // conv_tc3 MODE 2 (tap-table mode: the output-parity classes of a stride-2 data gradient, one per blockIdx.z,
+  // see conv_tc3.cu): class taps t < ntap read the gathered pixel (ho + dh[t], wo + dw[t]) with weight tap wt[t];
+  // output pixel (ho, wo) of the class lands at (2 ho + oph, 2 wo + opw) of the [B, OH, OW, N] tensor y
+  struct TapClass { int ntap, dh[4], dw[4], wt[4], oph, opw; };
+  TapClass cl[4];
+  int ncls, OH, OW;
 };
 // device buffer registered by fd_debug_set_conv_trace (conv_tc2.cu), or null
 extern long long* g_conv_trace_host;
@@ -28,6 +34,9 @@ int conv_tc2_dispatch(const TcArgs& a, int mode, cudaStream_t st);
 // conv_tc3.cu: the same with the input patch fetched once per 32-channel chunk by TMA and W_lo computed in
 // shared memory (stride-1 layers whose patch fits); returns -1 when it does not take the problem
 int conv_tc3_dispatch(const TcArgs& a, int mode, cudaStream_t st);
+// stride-2 data gradient as four stride-1 tap-table convolutions over dY, one per output-parity class (conv_tc3.cu);
+// a holds the plain dgrad problem (x = dY, w = W^T, y = dX, Ho x Wo = the full input size); -1 = not taken
+int conv_tc3_dgrad_s2(const TcArgs& a, cudaStream_t st);
 // conv_tc4.cu: persistent variant of conv_tc3 (epilogue overlapped with the next tile) for launches with more
 // tiles than SMs; returns -1 when it does not take the problem
 int conv_tc4_dispatch(const TcArgs& a, int mode, cudaStream_t st);

@@ -41,6 +41,11 @@ CONV_CASES = [
     (5, 32, 40, 100, 128, 3, 1, 1, True, "relu"),    # 160 tiles with a ragged last tile per image, BN = 128, odd nk
     (4, 96, 50, 100, 64, 1, 1, 0, True, "none"),     # 1x1: a chunk per k-block, 3 k-blocks per tile (group parity flips)
     (6, 32, 30, 130, 32, 3, 1, 0, True, "elu"),      # BN = 32, valid conv: the pad-0 data gradient steps backwards
+    # stride-2 data gradient as four output-parity classes (conv_tc3 tap-table mode) / its fallbacks
+    (3, 128, 24, 80, 256, 3, 2, 1, False, "none"),   # layer3.0 conv1: 1, 2, 2 and 4 taps per class, several tiles per image
+    (2, 32, 10, 18, 64, 3, 2, 1, True, "relu"),      # classes smaller than a tile, dX channels = 32
+    (2, 64, 15, 23, 128, 3, 2, 1, False, "none"),    # odd size: not taken (conv_tc2 masks the taps)
+    (2, 128, 12, 20, 64, 1, 2, 0, False, "none"),    # 1x1 / 2 downsample: one class, the other three are zero
 ]
 
 
