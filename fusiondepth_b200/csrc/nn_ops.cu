@@ -225,7 +225,17 @@ inline BnGeom bn_geom(long M, int C, int vec, bool reduce = false) {
   // statistic kernels: every block leaves one partial row (2*C doubles) for the last block of its channel
   // column to fold, so a few blocks per SM stream the tensor at L2 speed without contended atomics
   long cap = reduce ? (148L * 2 + bx - 1) / bx : (148L * 8 + bx - 1) / bx;
-  if (reduce && cap > BN_MAX_PARTS) cap = BN_MAX_PARTS;
+  // Partial rows: L2-sized tensors stream just as fast through ~96 blocks (and leave the SMs to the concurrent
+  // branches of the step: 96 / 148 / 296 measured within noise, 497-502 images/s); tensors far beyond L2 (the
+  // ResNet-50 layers at 1024x320, the stem) are HBM-bound and want two blocks per SM.  FD_BN_PARTS overrides.
+  static int parts_env = -2;
+  if (parts_env == -2) {
+    const char* e = getenv("FD_BN_PARTS");
+    parts_env = e ? atoi(e) : -1;
+    if (parts_env > BN_MAX_PARTS) parts_env = BN_MAX_PARTS;
+  }
+  const long parts_cap = parts_env > 0 ? parts_env : (M * C * 4L < (32L << 20) ? 96 : BN_MAX_PARTS);
+  if (reduce && cap > parts_cap) cap = parts_cap;
   if (by > cap) by = cap;
   if (by < 1) by = 1;
   g.grid = dim3(bx, (unsigned)by);

@@ -598,6 +598,7 @@ class InputFeeder:
         self.copy_stream = torch.cuda.Stream(device=step.flat.data.device)
         self.staging_inputs = [{k: torch.empty_like(v) for k, v in b.items()} for b in step.static_inputs]
         self.staging_noise = [{k: torch.empty_like(v) for k, v in n.items()} for n in step.static_noise]
+        self._pairs = None
         self.ready = torch.cuda.Event()
         self.consumed = torch.cuda.Event()
         self.consumed.record(torch.cuda.current_stream())
@@ -616,10 +617,14 @@ class InputFeeder:
     def commit(self):
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ready)
-        for dst, src in zip(self.step.static_inputs, self.staging_inputs):
-            for k in dst:
-                dst[k].copy_(src[k], non_blocking=True)
-        for dst, src in zip(self.step.static_noise, self.staging_noise):
-            for k in dst:
-                dst[k].copy_(src[k], non_blocking=True)
+        if self._pairs is None:
+            dsts, srcs = [], []
+            for dst, src in zip(list(self.step.static_inputs) + list(self.step.static_noise),
+                                list(self.staging_inputs) + list(self.staging_noise)):
+                for k in dst:
+                    dsts.append(dst[k])
+                    srcs.append(src[k])
+            self._pairs = (dsts, srcs)
+        # one multi-tensor copy instead of ~60 small launches between two graph replays
+        torch._foreach_copy_(self._pairs[0], self._pairs[1])
         self.consumed.record(cur)
