@@ -52,7 +52,7 @@ def conv_bn(conv, bn, x, residual=None, relu=False):
     ws = None
     if (bn.training or not bn.track_running_stats) and ops.conv_emits_stats(
             conv.in_channels, conv.out_channels, conv.bias is not None):
-        ws = torch.zeros(2 * conv.out_channels, device=x.device, dtype=torch.float64)
+        ws = ops.zeroed_stats(2 * conv.out_channels, x.device)
     return bn(conv(x, stats=ws), residual=residual, relu=relu, stats=ws)
 
 

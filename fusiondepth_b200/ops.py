@@ -31,6 +31,41 @@ DIRECT_GRAD = False
 WEIGHT_CACHE: Optional[Dict] = None
 
 
+class StatsArena:
+    """Zeroed fp64 scratch for the conv-epilogue BatchNorm statistics of one optimiser step.  Every conv + BN pair
+    used to allocate and zero its own [2*C] buffer (228 FillFunctor launches per ResNet-18 step); TrainStep
+    zeroes this arena ONCE at the start of the step and the pairs take consecutive 256-byte-aligned slices (host
+    side bump pointer: the call order is the same every step, so a captured graph sees fixed addresses)."""
+
+    def __init__(self, device, nbytes: int = 16 << 20):
+        self.buf = torch.zeros(nbytes // 8, device=device, dtype=torch.float64)
+        self.off = 0
+
+    def begin_step(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, n: int):
+        n_al = (n + 31) // 32 * 32
+        if self.off + n_al > self.buf.numel():
+            return None
+        t = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return t
+
+
+STATS_ARENA: Optional[StatsArena] = None
+
+
+def zeroed_stats(n: int, device) -> torch.Tensor:
+    """A zeroed float64 [n] buffer for fd_conv2d_fwd_tc_stats: a slice of the step's arena when one is active."""
+    if STATS_ARENA is not None:
+        t = STATS_ARENA.take(n)
+        if t is not None:
+            return t
+    return torch.zeros(n, device=device, dtype=torch.float64)
+
+
 def _direct_grad(p):
     return getattr(p, "_fd_grad", None) if (DIRECT_GRAD and p is not None) else None
 

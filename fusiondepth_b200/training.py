@@ -403,6 +403,7 @@ class TrainStep:
         self.mb_streams = [torch.cuda.Stream(device=dev) for _ in range(nsets)] if self.concurrent else []
         self.streams = self.trunks[0]
         self.bn_schedule = self._make_bn_schedule() if self.concurrent or parallel_trunks else None
+        self.stats_arena = None
         self.stream = torch.cuda.Stream(device=dev)      # warm-up and capture share one stream
         self.graph = None
         self.static_inputs = None
@@ -453,6 +454,10 @@ class TrainStep:
         ops.WEIGHT_CACHE = {} if self.cache_weight_prep else None
         ops.BN_SCHEDULE = self.bn_schedule
         ops.WGRAD_STREAMS = self.wgrad_streams
+        if self.stats_arena is None:
+            self.stats_arena = ops.StatsArena(self.flat.data.device)
+        ops.STATS_ARENA = self.stats_arena
+        self.stats_arena.begin_step()                 # one memset for every conv + BN pair of the step
         if self.bucketed:
             self._ready = [[] for _ in range(N_BUCKETS)]
             ops.GRAD_READY = self._grad_ready
@@ -469,6 +474,7 @@ class TrainStep:
             ops.DIRECT_GRAD = False
             ops.WEIGHT_CACHE = None
             ops.BN_SCHEDULE = None
+            ops.STATS_ARENA = None
             ops.GRAD_READY = None
             ops.WGRAD_STREAMS = None
 

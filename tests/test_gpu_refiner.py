@@ -151,8 +151,11 @@ def test_r50_train_vs_reference_fixture(cuda):
             got, want = float(dict(mods[name].named_parameters())[pk].grad.double().norm()), float(g[key])
             n += 1
             # 1e-2: the beam encoder sees a 90 %-empty input and B*H*W is small here, so its BatchNorm
-            # gradients are sums with heavy cancellation (measured up to 0.7 % off; trunk conv weights < 0.2 %)
-            if abs(got - want) > 1e-2 * want + 1e-9:
+            # gradients are sums with heavy cancellation (trunk conv weights < 0.2 % off).  The beam encoder's
+            # BatchNorm scale / shift gradients move from run to run with the order of the fp32 atomic adds in the
+            # weight-gradient and statistic kernels (0.3 ... 1.1 % observed over repeated runs): 2e-2 for those.
+            tol = 2e-2 if (name == "benc" and (".bn" in pk or "downsample.1" in pk)) else 1e-2
+            if abs(got - want) > tol * want + 1e-9:
                 bad.append((key, got, want))
         elif key.startswith("buf:"):
             name, pk = key[4:].split("/", 1)
