@@ -117,3 +117,49 @@ def test_process_batch_bench_size_vs_oracle(cuda):
             if abs(got - want) > tol * want + 1e-9:
                 bad.append((name, k, got, want))
     assert checked == 12 and not bad, bad[:10]
+
+
+def test_r50_process_batch_config3_resolution_vs_oracle(cuda):
+    """BASELINE config 3's networks at ITS resolution (ResNet-50, 1024x320; batch 2 of the 8 so that the CPU oracle
+    finishes in under a minute): the Bottleneck layer shapes of the bench (1x1 convs with 163 840 pixels per pair of
+    images through the persistent kernel, 2048-channel layer 4, stride-2 data gradients by parity class) --
+    losses, disparities, depths, poses < 1e-4, BN statistics, gradient norms."""
+    from fusiondepth_b200 import training
+    Bq, Hq, Wq = 2, 320, 1024
+    models = training.build_models(50, "cuda")
+    sds = {}
+    for i, (name, m) in enumerate(sorted(models.items())):
+        sds[name] = synth_weights(m.state_dict(), 900 + i)
+        m.load_state_dict(sds[name])
+        m.train()
+    osd = {k: clone_sd(v, requires_grad=True) for k, v in sds.items()}
+    inputs = synth.make_batch(Bq, Hq, Wq, seed=43, mode="coherent", lidar_density=0.03)
+    noise = inputs.pop("noise")
+    oo, ol = SO.process_batch(osd, inputs, noise, 50, training=True)
+    ol["loss"].backward()
+    outputs, losses = training.process_batch(models, synth.to_device(inputs, "cuda"),
+                                             {s: t.cuda() for s, t in noise.items()}, None, materialize=True)
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+    for k in ol:
+        assert rel_err(losses[k].detach().cpu(), ol[k].detach()) < 1e-4, (k, float(losses[k]), float(ol[k]))
+    for s in range(4):
+        assert rel_err(outputs[("disp", s)].detach().cpu(), oo[("disp", s)].detach()) < 1e-4, s
+        assert rel_err(outputs[("depth", 0, s)].detach().cpu(), oo[("depth", 0, s)].detach()) < 1e-4, s
+    for f in (-1, 1):
+        assert rel_err(outputs[("cam_T_cam", 0, f)].detach().cpu(), oo[("cam_T_cam", 0, f)].detach()) < 1e-5
+    for name in ("encoder", "depth"):
+        for k, b in models[name].named_buffers():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                assert rel_err(b.cpu(), osd[name][k]) < 1e-4, (name, k)
+    # gradient norms of the depth path (the pose networks' gradients at initialisation are tie-flip noise, see above)
+    bad = []
+    for name in ("depth", "encoder", "beam_encoder"):
+        for k, p in models[name].named_parameters():
+            og = osd[name][k].grad
+            if og is None:
+                continue
+            got, want = float(p.grad.double().norm()), float(og.double().norm())
+            if abs(got - want) > 2e-2 * want + 1e-9:
+                bad.append((name, k, got, want))
+    assert not bad, bad[:10]
