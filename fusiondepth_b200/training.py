@@ -165,18 +165,41 @@ def process_batch(models, inputs, noise=None, opts: Optional[Dict] = None, mater
     return outputs, losses
 
 
-def patch_trainer(trainer, materialize: bool = True):
-    """Swap the reference Trainer's warp + loss methods for the fused kernels, in place."""
-    opt = trainer.opt
+def _default_loss_config(opt, who):
     if (opt.v1_multiscale or opt.disable_automasking or opt.avg_reprojection or opt.no_ssim
             or opt.predictive_mask or opt.use_stereo or opt.pose_model_type == "posecnn"
             or list(opt.scales) != [0, 1, 2, 3] or list(opt.frame_ids) != [0, -1, 1]):
-        raise NotImplementedError("patch_trainer covers the reference's default loss configuration")
+        raise NotImplementedError("%s covers the reference's default loss configuration" % who)
+
+
+def patch_trainer(trainer, materialize: bool = True):
+    """Swap the reference Trainer's warp + loss methods for the fused kernels, in place."""
+    opt = trainer.opt
+    _default_loss_config(opt, "patch_trainer")
     opts = {"min_depth": opt.min_depth, "max_depth": opt.max_depth,
             "smoothness": opt.disparity_smoothness, "si_thresh": opt.gdc_loss_threshold,
             "si_var": opt.si_var, "use_si": opt.trainer_siloss == "true",
             # trainer.py:578: every scale with --trainer_siloss_all_scale (default on), else scale 0 only
             "si_scales": 0xF if opt.trainer_siloss_all_scale else 0x1}
+    return _patch_loss_methods(trainer, opt, opts, materialize)
+
+
+def patch_completor(completor, materialize: bool = True):
+    """The same for the completion driver (completor.py:426-474, 546-728): its loss code is a copy of the
+    trainer's with its own flags -- the si-loss (x26 depth, 4-beam target, 0.1 sqrt(mean d^2 - si_var mean(d)^2),
+    completor.py:694-715) on scale 0, or on every scale with --completion_siloss_all_scale true."""
+    opt = completor.opt
+    _default_loss_config(opt, "patch_completor")
+    if opt.completion_l1loss and not opt.completion_siloss:
+        raise NotImplementedError("patch_completor: --completion_l1loss is not part of the fused loss")
+    opts = {"min_depth": opt.min_depth, "max_depth": opt.max_depth,
+            "smoothness": opt.disparity_smoothness, "si_thresh": opt.gdc_loss_threshold,
+            "si_var": opt.si_var, "use_si": bool(opt.completion_siloss),
+            "si_scales": 0xF if opt.completion_siloss_all_scale == "true" else 0x1}
+    return _patch_loss_methods(completor, opt, opts, materialize)
+
+
+def _patch_loss_methods(trainer, opt, opts, materialize):
 
     def generate_images_pred(inputs, outputs, frame_ids):
         if len(frame_ids) > 1:

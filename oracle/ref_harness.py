@@ -46,9 +46,9 @@ def _purge():
 _cache = {}
 
 
-def load(dropin: bool = False, cpu_shim: bool = True, with_refiner: bool = False):
+def load(dropin: bool = False, cpu_shim: bool = True, with_refiner: bool = False, with_completor: bool = False):
     """Namespace with the reference's modules.  `dropin`: layers / networks come from this repo."""
-    key = (dropin, with_refiner)
+    key = (dropin, with_refiner, with_completor)
     if key in _cache:
         return _cache[key]
     ref = make_ref.root()
@@ -75,6 +75,8 @@ def load(dropin: bool = False, cpu_shim: bool = True, with_refiner: bool = False
         ns.trainer = importlib.import_module("trainer")
         if with_refiner:
             ns.refiner = importlib.import_module("refiner")
+        if with_completor:
+            ns.completor = importlib.import_module("completor")
     finally:
         sys.argv = argv
         sys.path[:] = old_path
@@ -150,6 +152,18 @@ def make_refiner(ns, models, B, H, W, device="cpu"):
         for val in ("False", "True"):
             rf.catxy[val, s] = ns.layers.Cat_xy(B, H >> s, W >> s).to(device)
     return rf
+
+
+def make_completor(ns, models, B, H, W, device="cpu"):
+    """object.__new__(Completor) wired by hand (completor.py:28-186 minus W&B / KITTI files and the forced
+    1216x352 size, completor.py:31-34: the drop-in test runs it at a size the CPU reference finishes in seconds).
+    Default flags: beam encoder, separate_resnet pose network, automasking, completion_siloss on scale 0."""
+    C = ns.completor
+    cp = object.__new__(C.Completor)
+    opt = copy.deepcopy(C.opts)
+    opt.batch_size = B
+    _wire(cp, opt, models, B, H, W, device, ns)
+    return cp
 
 
 class FixedNoise:

@@ -111,6 +111,38 @@ def gen_step(ns, B=3, H=96, W=160):
     print("step_r18", {k: float(v) for k, v in losses.items()})
 
 
+def gen_completor(B=2, H=96, W=160):
+    """Completor.process_batch + backward (completor.py:268-321, 546-728: the completion driver's step; the same
+    networks and layers.* surface as the trainer, its own copy of the loss code)."""
+    ns = RH.load(with_completor=True)
+    models = RH.make_models(ns, 18)
+    _load_weights(models, 3)
+    for m in models.values():
+        m.train()
+    cp = RH.make_completor(ns, models, B, H, W)
+    inputs = synth.make_batch(B, H, W, seed=6, mode="coherent", lidar_density=0.25)
+    noise = inputs.pop("noise")
+    with RH.FixedNoise([noise[s] for s in range(4)]):
+        outputs, losses = cp.process_batch(dict(inputs))
+    losses["loss"].backward()
+    out = {}
+    for s in range(4):
+        out["disp%d" % s] = outputs[("disp", s)].detach().numpy()
+        out["identity_selection%d" % s] = outputs["identity_selection/%d" % s].numpy()
+        out["depth%d" % s] = outputs[("depth", 0, s)].detach().numpy()
+    for f in (-1, 1):
+        out["cam_T_cam%d" % f] = outputs[("cam_T_cam", 0, f)].detach().numpy()
+        out["color%d_0" % f] = outputs[("color", f, 0)].detach().numpy()
+    for k, v in losses.items():
+        out["loss:" + k] = v.detach().numpy()
+    for name, m in sorted(models.items()):
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                out["gnorm:%s/%s" % (name, k)] = p.grad.double().norm().numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "step_completor.npz"), **out)
+    print("step_completor", {k: float(v) for k, v in losses.items()})
+
+
 def gen_forward_variants(ns, H=64, W=96):
     """Config 1 (enc+beam enc+decoder forward, eval mode) for R18 and R50, plus the stage-2
     refine2d decoder (road,catxy,deep) and PoseCNN forward."""
@@ -336,9 +368,11 @@ if __name__ == "__main__":
     assert RH.available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN, exist_ok=True)
     ns = RH.load()
-    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss", "keys", "refiner", "r50"]
+    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss", "keys", "refiner", "r50", "completor"]
     if "refiner" in which:
         gen_refiner()
+    if "completor" in which:
+        gen_completor()
     if "r50" in which:
         gen_r50_train()
     if "keys" in which:

@@ -135,3 +135,53 @@ def test_unchanged_refiner_dropin(cuda):
                 if abs(got - want) > _gtol(key) * want + 1e-9:
                     bad.append((key, got, want))
         assert not bad, (patched, bad[:8])
+
+
+@pytest.mark.parametrize("patched", [False, True])
+def test_unchanged_completor_dropin(cuda, patched):
+    """The completion driver (driver half): the reference's UNCHANGED completor.py --
+    Completor.process_batch + backward -- against fusiondepth_b200/dropin, unpatched (every layers.* / F.* call of
+    its loss code on this library's kernels) and with patch_completor (fused loss), vs the fixture the reference
+    itself produced (tests/make_golden.py gen_completor)."""
+    from fusiondepth_b200 import training
+    if not RH.available():
+        pytest.skip("reference sources not staged (oracle/_ref)")
+    g = np.load(GOLDEN + "/step_completor.npz")
+    ns = RH.load(dropin=True, with_completor=True)
+    assert ns.networks.ResnetEncoder.__module__.startswith("fusiondepth_b200"), "drop-in did not resolve"
+    assert ns.completor.__file__.startswith(ns.root), "completor.py must be the reference's own file"
+    models = RH.make_models(ns, 18)
+    for i, (name, m) in enumerate(sorted(models.items())):
+        m.load_state_dict(synth_weights(m.state_dict(), 300 + i))
+        m.cuda().train()
+    cp = RH.make_completor(ns, models, 2, 96, 160, device="cuda")
+    if patched:
+        training.patch_completor(cp)
+    inputs = synth.make_batch(2, 96, 160, seed=6, mode="coherent", lidar_density=0.25)
+    noise = inputs.pop("noise")
+    with RH.FixedNoise([noise[s] for s in range(4)]):
+        outputs, losses = cp.process_batch(dict(inputs))
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+    for key in g.files:
+        if key.startswith("loss:"):
+            k = key[5:]
+            assert rel_err(losses[k].detach().cpu(), g[key]) < 1e-4, (k, float(losses[k]), float(g[key]))
+    for s in range(4):
+        assert rel_err(outputs[("disp", s)].detach().cpu(), g["disp%d" % s]) < 1e-4, s
+        assert rel_err(outputs[("depth", 0, s)].detach().cpu(), g["depth%d" % s]) < 1e-4, s
+        mism = (outputs["identity_selection/%d" % s].cpu().numpy() != g["identity_selection%d" % s]).mean()
+        assert mism < 1e-3, (s, mism)
+    for f in (-1, 1):
+        assert rel_err(outputs[("cam_T_cam", 0, f)].detach().cpu(), g["cam_T_cam%d" % f]) < 1e-5
+        assert rel_err(outputs[("color", f, 0)].detach().cpu(), g["color%d_0" % f]) < 2e-4
+    bad, n = [], 0
+    for key in g.files:
+        if key.startswith("gnorm:"):
+            name, pk = key[6:].split("/", 1)
+            p = dict(models[name].named_parameters())[pk]
+            got, want = float(p.grad.double().norm()), float(g[key])
+            n += 1
+            if abs(got - want) > _gtol(key) * want + 1e-9:
+                bad.append((key, got, want))
+    assert n > 200 and not bad, bad[:8]

@@ -101,3 +101,25 @@ def test_compute_depth_losses_matches_trainer(cuda):
     evaluation.compute_depth_losses({"depth_gt": gt.cuda()}, {("depth", 0, 0): depth.cuda()}, losses)
     got = [float(losses[k]) for k in evaluation.DEPTH_METRIC_NAMES]
     assert np.allclose(got, want, rtol=2e-5, atol=1e-7), (got, want)
+
+
+def test_folded_forward_at_completion_resolution(cuda):
+    """The completion driver's working size (completor.py:31-34 forces 352 x 1216): BN-folded encoder + beam encoder
+    + decoder forward against the CPU oracle's eval-mode forward on the same input."""
+    from fusiondepth_b200 import evaluation, synth
+    H, W = 352, 1216
+    models = _eval_models(18)
+    g = torch.Generator().manual_seed(3)
+    rgb = torch.rand(1, 3, H, W, generator=g)
+    two = torch.zeros(1, 2, H, W)
+    mask = torch.rand(1, 1, H, W, generator=g) < 0.03
+    two[:, 0:1] = mask * torch.rand(1, 1, H, W, generator=g) * 0.6
+    two[:, 1:2] = mask.float()
+    sds = {k: {n: t.detach().cpu() for n, t in m.state_dict().items()} for k, m in models.items()}
+    with torch.no_grad():
+        feats = SO.resnet_encoder(sds["encoder"], rgb, 18, training=False)
+        beam = SO.resnet_encoder(sds["beam_encoder"], two, 18, training=False)
+        ref = SO.disp_to_depth(SO.depth_decoder(sds["depth"], feats, beam_feats=beam)[("disp", 0)], 0.1, 100.0)[0][:, 0]
+    run = evaluation.EvalRunner(models, 1, H, W)
+    disp = run({("color", 0, 0): rgb.cuda(), "2channel": two.cuda()})
+    assert rel_err(disp.cpu(), ref) < 1e-4

@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 900 python -m pytest tests/test_gpu_eval.py -m gpu -q --tb=short -p no:cacheprovider 2>&1 | tail -8 | cut -c1-300
