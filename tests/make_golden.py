@@ -143,6 +143,79 @@ def gen_completor(B=2, H=96, W=160):
     print("step_completor", {k: float(v) for k, v in losses.items()})
 
 
+def gdc_scene(H=120, W=400, seed=0):
+    """Synthetic road scene for GDC: ground plane 1.65 m below the camera, a wall at 40 m, two boxes; the
+    prediction is the truth with a smooth ~4 % error, the LiDAR ground truth four sparse scan lines of the truth."""
+    rng = np.random.RandomState(seed)
+    f, cu, cv = 290.0, W / 2.0 - 0.5, H * 0.45
+    v, u = np.mgrid[0:H, 0:W].astype(np.float64)
+    with np.errstate(divide="ignore"):
+        ground = np.where(v > cv + 1, 1.65 * f / np.maximum(v - cv, 1e-6), 1e9)
+    true = np.minimum(ground, 40.0)
+    for (u0, u1, z) in ((60, 110, 12.0), (250, 300, 22.0)):
+        box = (u >= u0) & (u < u1) & (ground > z) & (v > cv - 20)
+        true = np.where(box, z, true)
+    err = 1.0 + 0.04 * np.sin(u / 37.0) * np.cos(v / 23.0) + 0.003 * rng.randn(H, W)
+    pred = true * err
+    gt = np.full((H, W), -1.0)
+    for row in (int(cv) + 6, int(cv) + 11, int(cv) + 19, int(cv) + 33):
+        cols = np.arange(3, W - 3, 3) + rng.randint(0, 2, size=len(np.arange(3, W - 3, 3)))
+        gt[row, cols] = true[row, cols] * (1.0 + 0.002 * rng.randn(len(cols)))
+    calib_txt = ("R_rect_00: 1 0 0 0 1 0 0 0 1\nP_rect_02: %r 0 %r 13.0 0 %r %r 0.5 0 0 1 0.003\n"
+                 "P_rect_03: %r 0 %r -100.0 0 %r %r 0.5 0 0 1 0.003\n" % (f, cu, f, cv, f, cu, f, cv))
+    return pred, gt, calib_txt
+
+
+def gen_gdc():
+    """The reference's own GDC (gdc_old.py:74-250) on two synthetic scenes, run under two third-party API shims
+    (none edits a reference file): pykdtree.kdtree.KDTree -> scipy.spatial.cKDTree (pykdtree is not installed;
+    both are exact kNN), the `tol=` keyword of scipy.sparse.linalg.cg, removed in SciPy 1.14 -> `rtol=`, and
+    NumPy 1.x's stacked-vector reading of np.linalg.solve(As, bs)."""
+    import tempfile
+    import types
+    import scipy.sparse.linalg as spl
+    from scipy.spatial import cKDTree
+    kd = types.ModuleType("pykdtree.kdtree")
+    kd.KDTree = cKDTree
+    sys.modules.setdefault("pykdtree", types.ModuleType("pykdtree"))
+    sys.modules["pykdtree.kdtree"] = kd
+    sys.modules.setdefault("open3d", types.ModuleType("open3d"))
+    ref = RH.make_ref.root()
+    sys.path.insert(0, ref)
+    try:
+        import importlib
+        gdc_old = importlib.import_module("gdc_old")
+        pse = importlib.import_module("kitti_util_from_pse")
+    finally:
+        sys.path.remove(ref)
+    gdc_old.cg = lambda A, b, x0=None, tol=1e-5: spl.cg(A, b, x0=x0, rtol=tol)
+    # third shim: NumPy 2 reads a (N, M) right-hand side next to (N, M, M) matrices as ONE matrix; the reference
+    # was written for NumPy 1.x, where it is a stack of N vectors (gdc_old.py:186)
+    real_solve = np.linalg.solve
+
+    def solve_np1(a, b):
+        return real_solve(a, b[..., None])[..., 0] if b.ndim == a.ndim - 1 else real_solve(a, b)
+
+    gdc_old.np = types.SimpleNamespace(**{k: getattr(np, k) for k in dir(np) if not k.startswith("__")})
+    gdc_old.np.linalg = types.SimpleNamespace(**{k: getattr(np.linalg, k) for k in dir(np.linalg) if not k.startswith("__")})
+    gdc_old.np.linalg.solve = solve_np1
+    out = {}
+    for i, (seed, rng_deg) in enumerate(((0, (-0.1, 4.0)), (1, (-1.5, 9.0)))):
+        pred, gt, calib_txt = gdc_scene(seed=seed)
+        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as fh:
+            fh.write(calib_txt)
+        calib = pse.Calibration(fh.name)
+        os.unlink(fh.name)
+        corrected = gdc_old.GDC(pred.copy(), gt.copy(), calib, W_tol=3e-5, recon_tol=5e-4, k=10, method="cg",
+                                verbose=False, consider_range=rng_deg)          # inf_gdc.py:81
+        out["pred%d" % i], out["gt%d" % i], out["corrected%d" % i] = pred, gt, corrected
+        out["calib%d" % i] = np.array([calib.c_u, calib.c_v, calib.f_u, calib.f_v, calib.b_x, calib.b_y])
+        out["range%d" % i] = np.array(rng_deg)
+        print("gdc scene %d: changed pixels %d, mean |corr - pred| %.4f" % (
+            i, int((corrected != pred).sum()), float(np.abs(corrected - pred).mean())))
+    np.savez_compressed(os.path.join(GOLDEN, "gdc.npz"), **out)
+
+
 def gen_forward_variants(ns, H=64, W=96):
     """Config 1 (enc+beam enc+decoder forward, eval mode) for R18 and R50, plus the stage-2
     refine2d decoder (road,catxy,deep) and PoseCNN forward."""
@@ -368,11 +441,13 @@ if __name__ == "__main__":
     assert RH.available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN, exist_ok=True)
     ns = RH.load()
-    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss", "keys", "refiner", "r50", "completor"]
+    which = sys.argv[1:] or ["lidar", "step", "fwd", "loss", "keys", "refiner", "r50", "completor", "gdc"]
     if "refiner" in which:
         gen_refiner()
     if "completor" in which:
         gen_completor()
+    if "gdc" in which:
+        gen_gdc()
     if "r50" in which:
         gen_r50_train()
     if "keys" in which:
