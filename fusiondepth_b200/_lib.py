@@ -45,6 +45,7 @@ class Segment(ctypes.Structure):
 
 
 _I, _L, _F, _P = c_int, c_long, c_float, c_void_p
+_D = ctypes.c_double
 
 _SIGNATURES = {
     "fd_last_error": (c_char_p, []),
@@ -119,6 +120,15 @@ _SIGNATURES = {
     "fd_resize_lanczos_u8": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
     "fd_color_jitter_u8": (c_int, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "fd_image_to_tensor": (c_int, [_P, _P, _I, _I, _I, _P]),
+    "fd_gdc_select": (c_int, [_P, _P, _I, _I, _P, _D, _D, _P, _P, _P]),
+    "fd_gdc_knn": (c_int, [_P, _I, _I, _P, _P]),
+    "fd_gdc_weights": (c_int, [_P, _P, _I, _I, _D, _P, _P]),
+    "fd_gdc_rhs": (c_int, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "fd_gdc_apply": (c_int, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "fd_gdc_apply_t": (c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "fd_gdc_dot": (c_int, [_P, _P, _I, _P, _P]),
+    "fd_gdc_cg_update": (c_int, [_P, _P, _P, _P, _I, _P, _P]),
+    "fd_gdc_cg_dir": (c_int, [_P, _P, _I, _P, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

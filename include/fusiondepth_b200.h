@@ -343,6 +343,37 @@ int fd_color_jitter_u8(unsigned char* img, int B, int H, int W, const int* order
                        unsigned long long* lum_sums, void* stream);
 int fd_image_to_tensor(const unsigned char* img, float* out, int B, int H, int W, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Graph-based Depth Correction: gdc_old.py:74-250 as called by inf_gdc.py:81
+ * (k = 10, W_tol = 3e-5, recon_tol = 5e-4, method = 'cg'); fp64 throughout, like the reference.
+ *
+ * fd_gdc_select: pred, gt [H,W] (gt <= 0: no return) -> cls [H*W] uint8 (0 untouched, 1 pseudo-LiDAR point to
+ *   correct = gdc_old.py `pred_mask`, 2 LiDAR anchor = `gt_mask`) and points [H*W,3] (back-projection with the
+ *   PREDICTED depth, kitti_util_from_pse.py:204-215; calib6 = c_u, c_v, f_u, f_v, b_x, b_y on the host;
+ *   th_lo / th_hi = radians(consider_range)).  The caller orders the points class 1 first, then class 2, each in
+ *   raster order (gdc_old.py:163-168).
+ * fd_gdc_knn: exact k nearest neighbours of every point among the others, ascending distance (:171-172).
+ * fd_gdc_weights: the (k+2)x(k+2) constrained reconstruction systems (:174-186) -> weights [n,k].
+ * fd_gdc_rhs / fd_gdc_apply / fd_gdc_apply_t: b, y = A x, z = A^T y for A = [I - W_PLPL ; W_PLL] (:196-222);
+ *   entries / col_ptr: the (row, slot) indices with neighbour < n_pl, sorted by neighbour (rows ascending).
+ * fd_gdc_dot / fd_gdc_cg_update / fd_gdc_cg_dir: the conjugate-gradient recurrence of scipy.sparse.linalg.cg on
+ *   device scalars scal = {rho, p.q, rho_new}: update: x += (rho / p.q) p, r -= (rho / p.q) q, rho_new = r.r;
+ *   dir: p = r + (rho_new / rho) p, rho = rho_new.  One block each: fixed summation order. */
+int fd_gdc_select(const double* pred, const double* gt, int H, int W, const double* calib6_host, double th_lo,
+                  double th_hi, unsigned char* cls, double* points, void* stream);
+int fd_gdc_knn(const double* points, int n, int k, int* neighbors, void* stream);
+int fd_gdc_weights(const double* x_info, const int* neighbors, int n, int k, double w_tol, double* weights,
+                   void* stream);
+int fd_gdc_rhs(const double* weights, const int* neighbors, int n, int n_pl, int k, const double* gt_info, double* b,
+               void* stream);
+int fd_gdc_apply(const double* weights, const int* neighbors, int n, int n_pl, int k, const double* x, double* y,
+                 void* stream);
+int fd_gdc_apply_t(const double* weights, const long* entries, const long* col_ptr, int n_pl, int k,
+                   const double* y, double* z, void* stream);
+int fd_gdc_dot(const double* a, const double* b, int n, double* out, void* stream);
+int fd_gdc_cg_update(double* x, double* r, const double* p, const double* q, int n, double* scal, void* stream);
+int fd_gdc_cg_dir(double* p, const double* r, int n, double* scal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
