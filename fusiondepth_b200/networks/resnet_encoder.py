@@ -139,6 +139,42 @@ class ResNetTrunk(nn.Module):
         return nn.Sequential(*layers)
 
 
+def find_imagenet_checkpoint(num_layers):
+    """Path of torchvision's ``resnet{N}-<hash>.pth`` on local disk.  The reference downloads it
+    (model_zoo.load_url, resnet_encoder.py:46 / torchvision's ``pretrained=True``); this package never opens a
+    socket, so the file has to be in $FD_PRETRAINED_DIR or in torch.hub's checkpoint cache already."""
+    import glob
+    import os
+    dirs = [os.environ.get("FD_PRETRAINED_DIR"),
+            os.path.join(torch.hub.get_dir(), "checkpoints")]
+    for d in dirs:
+        if d:
+            hits = sorted(glob.glob(os.path.join(d, "resnet%d-*.pth" % num_layers)))
+            if hits:
+                return hits[0]
+    raise RuntimeError(
+        "pretrained=True: no resnet%d-*.pth under %s; copy torchvision's ImageNet checkpoint there "
+        "(or set FD_PRETRAINED_DIR), or construct with pretrained=False (--weights_init scratch) and "
+        "load a checkpoint via load_state_dict" % (num_layers, [d for d in dirs if d]))
+
+
+def load_imagenet_weights(trunk, num_layers, num_input_images=1, keep_conv1=True):
+    """Fill a ResNetTrunk from torchvision's ImageNet state dict (same keys).  conv1 is repeated over the
+    stacked input frames and divided by their number (resnet_encoder.py:47-48); with keep_conv1=False the
+    trunk's own (replaced, randomly initialised) conv1 stays."""
+    loaded = torch.load(find_imagenet_checkpoint(num_layers), map_location="cpu", weights_only=True)
+    loaded = dict(loaded)
+    if keep_conv1:
+        if num_input_images > 1:
+            loaded["conv1.weight"] = torch.cat([loaded["conv1.weight"]] * num_input_images, 1) / num_input_images
+    else:
+        loaded["conv1.weight"] = trunk.conv1.weight.detach()
+    trunk.load_state_dict(loaded)
+    for m in trunk.modules():        # load_state_dict copies into the existing storage; keep the NHWC layout explicit
+        if isinstance(m, nn.Conv2d):
+            m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+
+
 class ResnetEncoder(nn.Module):
     """Pytorch-module-compatible ResNet encoder (reference resnet_encoder.py:53-103)."""
 
@@ -148,9 +184,6 @@ class ResnetEncoder(nn.Module):
         self.num_ch_enc = np.array([64, 64, 128, 256, 512])
         if num_layers not in BLOCKS:
             raise ValueError("{} is not a valid number of resnet layers".format(num_layers))
-        if pretrained:
-            raise RuntimeError("pretrained ImageNet weights need a download; construct with "
-                               "pretrained=False and load a checkpoint via load_state_dict")
         # conv1 input channels: resnet_encoder.py:71-87
         cin = 3 * num_input_images if num_input_images > 1 else 3
         if cat4beam_to_color:
@@ -163,6 +196,11 @@ class ResnetEncoder(nn.Module):
             cin = 6
         self.num_layers = num_layers
         self.encoder = ResNetTrunk(num_layers, cin)
+        if pretrained:
+            # resnet_encoder.py:45-49, 71-87: the ImageNet weights go in first (conv1 tiled over the stacked
+            # frames), then the 4/5/2/6-channel variants replace conv1 by a freshly initialised one
+            keep_conv1 = cin == (3 * num_input_images if num_input_images > 1 else 3)
+            load_imagenet_weights(self.encoder, num_layers, num_input_images, keep_conv1)
         if num_layers > 34:
             self.num_ch_enc[1:] *= 4
 

@@ -89,3 +89,39 @@ def test_torch_composed_layers_match_oracle():
     assert L.F.relu is torch.nn.functional.relu and L.F.max_pool2d is torch.nn.functional.max_pool2d
     y = L.F.interpolate(disp, [2 * H, 2 * W], mode="bilinear", align_corners=False)      # CPU: torch's own
     assert torch.equal(y, torch.nn.functional.interpolate(disp, [2 * H, 2 * W], mode="bilinear", align_corners=False))
+
+
+def test_pretrained_loads_local_imagenet_checkpoint(tmp_path, monkeypatch):
+    """resnet_encoder.py:45-49, 71-87: ImageNet weights (here a stand-in state dict with torchvision's keys),
+    conv1 tiled over the stacked frames and divided by their number; the 2/4/5/6-channel variants keep a fresh
+    conv1.  No file -> a RuntimeError naming the directories (the package never downloads)."""
+    import fusiondepth_b200.networks as N
+    from fusiondepth_b200.networks.resnet_encoder import ResNetTrunk
+    monkeypatch.setenv("FD_PRETRAINED_DIR", str(tmp_path))
+    monkeypatch.setattr(torch.hub, "get_dir", lambda: str(tmp_path / "nohub"))
+    try:
+        N.ResnetEncoder(18, True)
+        assert False, "expected RuntimeError"
+    except RuntimeError as e:
+        assert "resnet18-*.pth" in str(e) and str(tmp_path) in str(e)
+    torch.manual_seed(3)
+    src = ResNetTrunk(18, 3)
+    for p in src.parameters():
+        p.data.normal_()
+    sd = {k: v.clone().contiguous() for k, v in src.state_dict().items()}
+    torch.save(sd, tmp_path / "resnet18-0badc0de.pth")
+    one = N.ResnetEncoder(18, True)
+    pair = N.ResnetEncoder(18, True, num_input_images=2)
+    beam = N.ResnetEncoder(18, True, beam_encoder=True)
+    for enc in (one, pair, beam):
+        got = enc.encoder.state_dict()
+        assert set(got) == set(sd)
+        for k in sd:
+            if k != "conv1.weight":
+                assert torch.equal(got[k], sd[k]), k
+        for m in enc.encoder.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                assert m.weight.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(one.encoder.conv1.weight, sd["conv1.weight"])
+    assert torch.equal(pair.encoder.conv1.weight, torch.cat([sd["conv1.weight"]] * 2, 1) / 2)
+    assert tuple(beam.encoder.conv1.weight.shape) == (64, 2, 7, 7)
