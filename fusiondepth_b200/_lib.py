@@ -106,10 +106,14 @@ _SIGNATURES = {
     "fd_bn_workspace_bytes": (c_size_t, [_I]),
     "fd_bn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "fd_bn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "fd_bn_bwd_xmask_ok": (c_int, [_L, _I]),
+    "fd_bn_bwd_xmask": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _L, _I, _I, _P]),
     "fd_maxpool3x3s2_fwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_maxpool3x3s2_bwd": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "fd_assemble_fwd": (c_int, [POINTER(Segment), _I, _P, _I, _I, _I, _I, _P]),
     "fd_assemble_bwd": (c_int, [_P, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), _I, _I, _I, _I, _I, _P]),
+    "fd_assemble_bwd2": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int), _I, _I, _I, _I,
+                                 _I, _P]),
     "fd_add": (c_int, [_P, _P, _P, _L, _P]),
     "fd_add_relu": (c_int, [_P, _P, _P, _L, _P]),
     "fd_mean_hw_fwd": (c_int, [_P, _P, _I, _I, _I, _F, _P]),

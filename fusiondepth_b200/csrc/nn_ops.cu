@@ -330,6 +330,12 @@ __device__ __forceinline__ BnStat bn_channel_stat(const double* __restrict__ ws,
   return r;
 }
 
+// The normalise + affine expression with its rounding steps spelled out: the backward kernels re-evaluate it to
+// rebuild the ReLU mask from x (fd_bn_bwd_xmask), which only works if both sides round identically.
+__device__ __forceinline__ float bn_affine(float v, float mu, float rs, float g, float bt) {
+  return fmaf(__fmul_rn(__fsub_rn(v, mu), rs), g, bt);
+}
+
 // pass 2 (finalize folded in): y = relu?((x - mean) * rstd * gamma + beta [+ residual])
 template <int VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
@@ -354,7 +360,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
     if (res) ldv<VEC>(res + m * C + c, r);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      float o = (v[i] - mu[i]) * rs[i] * g[i] + bt[i];
+      float o = bn_affine(v[i], mu[i], rs[i], g[i], bt[i]);
       if (res) o += r[i];
       if (relu) o = fmaxf(o, 0.f);
       v[i] = o;
@@ -363,21 +369,26 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
-// backward pass 1: sum g, sum g*xhat with g = dy * relu_mask
+// backward pass 1: sum g, sum g*xhat with g = dy * relu_mask.  The mask is y > 0, with y either read back or
+// (y == nullptr, residual-free BatchNorm + ReLU) re-evaluated from x with mgamma / mbeta: one tensor read less.
 template <int VEC>
 __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                      const float* __restrict__ dy, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, int relu,
-                                     double* __restrict__ ws, long M, int C) {
+                                     double* __restrict__ ws, long M, int C,
+                                     const float* __restrict__ mgamma, const float* __restrict__ mbeta) {
   extern __shared__ double red[];
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   double s[VEC], ss[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s[i] = ss[i] = 0.0;
   if (c < C) {
-    float mu[VEC], rs[VEC];
+    float mu[VEC], rs[VEC], mg[VEC], mb[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { mu[i] = mean[c + i]; rs[i] = rstd[c + i]; }
+    for (int i = 0; i < VEC; ++i) {
+      mu[i] = mean[c + i]; rs[i] = rstd[c + i];
+      mg[i] = (relu && !y) ? mgamma[c + i] : 0.f; mb[i] = (relu && !y) ? mbeta[c + i] : 0.f;
+    }
     const long step = (long)gridDim.y * blockDim.y;
     for (long m0 = (long)blockIdx.y * blockDim.y + threadIdx.y; m0 < M; m0 += step * 4) {
       float ps[VEC], pss[VEC];
@@ -390,10 +401,11 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* _
           float xv[VEC], yv[VEC], gv[VEC];
           ldv<VEC>(x + m * C + c, xv);
           ldv<VEC>(dy + m * C + c, gv);
-          if (relu) ldv<VEC>(y + m * C + c, yv);
+          if (relu && y) ldv<VEC>(y + m * C + c, yv);
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
             float g = gv[i];
+            if (relu && !y) yv[i] = bn_affine(xv[i], mu[i], rs[i], mg[i], mb[i]);
             if (relu && !(yv[i] > 0.f)) g = 0.f;
             ps[i] += g;
             pss[i] = fmaf(g, (xv[i] - mu[i]) * rs[i], pss[i]);
@@ -435,13 +447,13 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
                                     int relu, int training, const double* __restrict__ ws,
                                     float* __restrict__ dx, float* __restrict__ dres,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long M,
-                                    int C, int accumulate) {
+                                    int C, int accumulate, const float* __restrict__ mbeta) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c >= C) return;
-  float mu[VEC], rs[VEC], gm[VEC], k1[VEC], k2[VEC];
+  float mu[VEC], rs[VEC], gm[VEC], k1[VEC], k2[VEC], mb[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    mu[i] = mean[c + i]; rs[i] = rstd[c + i]; gm[i] = gamma[c + i];
+    mu[i] = mean[c + i]; rs[i] = rstd[c + i]; gm[i] = gamma[c + i]; mb[i] = (relu && !y) ? mbeta[c + i] : 0.f;
     const float sg = (float)ws[c + i], sgx = (float)ws[C + c + i];
     k1[i] = training ? sg / (float)M : 0.f;
     k2[i] = training ? sgx / (float)M : 0.f;
@@ -460,9 +472,10 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
     float xv[VEC], yv[VEC], gv[VEC];
     ldv<VEC>(x + m * C + c, xv);
     ldv<VEC>(dy + m * C + c, gv);
-    if (relu) ldv<VEC>(y + m * C + c, yv);
+    if (relu && y) ldv<VEC>(y + m * C + c, yv);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
+      if (relu && !y) yv[i] = bn_affine(xv[i], mu[i], rs[i], gm[i], mb[i]);
       if (relu && !(yv[i] > 0.f)) gv[i] = 0.f;
     }
     if (dres) stv<VEC>(dres + m * C + c, gv);
@@ -768,6 +781,7 @@ struct AsmArgs {
   const float* a[MAXSEG];
   const float* b[MAXSEG];
   float* d[MAXSEG];
+  float* d2[MAXSEG];   // backward: optional second copy of d (the `b` operand's own gradient tensor)
   int C[MAXSEG], up[MAXSEG], off[MAXSEG];
   int nseg, Ctot, B, H, W, pad;
 };
@@ -827,6 +841,7 @@ __global__ void assemble_bwd_kernel(AsmArgs a, const float* __restrict__ dout, i
         }
       }
       a.d[s][p * Cs + c] = acc;
+      if (a.d2[s]) a.d2[s][p * Cs + c] = acc;
     }
   }
 }
@@ -884,6 +899,7 @@ __global__ void assemble_bwd_v4_kernel(AsmArgs a, const float* __restrict__ dout
       }
     }
     *reinterpret_cast<float4*>(a.d[s] + (long)i * 4) = acc;
+    if (a.d2[s]) *reinterpret_cast<float4*>(a.d2[s] + (long)i * 4) = acc;
   }
 }
 
@@ -1053,35 +1069,57 @@ int fd_bn_fwd(const float* x, const float* residual, const float* gamma, const f
   return 0;
 }
 
-int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
-              const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
-              float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
-              int accumulate, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (bn_fused_ok(M, C)) {
-    bn_bwd_fused_kernel<<<C / BNF_CG, 256, BNF_SMEM, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
-                                                          dx, dresidual, dgamma, dbeta, (int)M, C, accumulate);
-    FD_CHECK_LAUNCH();
-    return 0;
-  }
+static int bn_bwd_launch(const float* x, const float* y, const float* dy, const float* gamma, const float* mbeta,
+                         const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
+                         float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
+                         int accumulate, cudaStream_t st) {
   const int vec = (C % 4 == 0) ? 4 : 1;
   BnGeom g = bn_geom(M, C, vec);
   const size_t sm = sizeof(double) * 2 * vec * 256;
   BnGeom gr = bn_geom(M, C, vec, true);
   cudaMemsetAsync(ws + (size_t)(1 + BN_MAX_PARTS) * 2 * C, 0, sizeof(unsigned) * gr.grid.x, st);
   if (vec == 4) {
-    bn_bwd_reduce_kernel<4><<<gr.grid, gr.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
+    bn_bwd_reduce_kernel<4><<<gr.grid, gr.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C, gamma,
+                                                           mbeta);
     FD_CHECK_LAUNCH();
     bn_bwd_apply_kernel<4><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
-                                                       ws, dx, dresidual, dgamma, dbeta, M, C, accumulate);
+                                                       ws, dx, dresidual, dgamma, dbeta, M, C, accumulate, mbeta);
   } else {
-    bn_bwd_reduce_kernel<1><<<gr.grid, gr.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C);
+    bn_bwd_reduce_kernel<1><<<gr.grid, gr.block, sm, st>>>(x, y, dy, save_mean, save_rstd, relu, ws, M, C, gamma,
+                                                           mbeta);
     FD_CHECK_LAUNCH();
     bn_bwd_apply_kernel<1><<<g.grid, g.block, 0, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
-                                                       ws, dx, dresidual, dgamma, dbeta, M, C, accumulate);
+                                                       ws, dx, dresidual, dgamma, dbeta, M, C, accumulate, mbeta);
   }
   FD_CHECK_LAUNCH();
   return 0;
+}
+
+int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma,
+              const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
+              float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
+              int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  FD_REQUIRE(y != nullptr || !relu, "fd_bn_bwd: y is needed for the ReLU mask (or use fd_bn_bwd_xmask)");
+  if (bn_fused_ok(M, C)) {
+    bn_bwd_fused_kernel<<<C / BNF_CG, 256, BNF_SMEM, st>>>(x, y, dy, gamma, save_mean, save_rstd, relu, training,
+                                                          dx, dresidual, dgamma, dbeta, (int)M, C, accumulate);
+    FD_CHECK_LAUNCH();
+    return 0;
+  }
+  return bn_bwd_launch(x, y, dy, gamma, nullptr, save_mean, save_rstd, relu, training, dx, dresidual, dgamma, dbeta,
+                       ws, M, C, accumulate, st);
+}
+
+int fd_bn_bwd_xmask_ok(long M, int C) { return bn_fused_ok(M, C) ? 0 : 1; }
+
+int fd_bn_bwd_xmask(const float* x, const float* dy, const float* gamma, const float* beta,
+                    const float* save_mean, const float* save_rstd, int training, float* dx, float* dgamma,
+                    float* dbeta, double* ws, long M, int C, int accumulate, void* stream) {
+  FD_REQUIRE(!bn_fused_ok(M, C), "fd_bn_bwd_xmask: small tensors go through fd_bn_bwd (fd_bn_bwd_xmask_ok)");
+  FD_REQUIRE(gamma != nullptr && beta != nullptr, "fd_bn_bwd_xmask: gamma and beta are needed for the mask");
+  return bn_bwd_launch(x, nullptr, dy, gamma, beta, save_mean, save_rstd, 1, training, dx, nullptr, dgamma, dbeta,
+                       ws, M, C, accumulate, (cudaStream_t)stream);
 }
 
 int fd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C,
@@ -1121,7 +1159,7 @@ static int fill_asm(AsmArgs& a, int nseg, const int* C, const int* up, int B, in
   a.nseg = nseg; a.B = B; a.H = H; a.W = W; a.pad = pad;
   int off = 0;
   for (int i = 0; i < MAXSEG; ++i) {
-    a.a[i] = a.b[i] = nullptr; a.d[i] = nullptr;
+    a.a[i] = a.b[i] = nullptr; a.d[i] = a.d2[i] = nullptr;
     a.C[i] = i < nseg ? C[i] : 0;
     a.up[i] = i < nseg ? up[i] : 0;
     a.off[i] = off;
@@ -1160,15 +1198,25 @@ int fd_assemble_fwd(const fd_segment* segs, int nseg, float* out, int B, int H, 
 
 int fd_assemble_bwd(const float* dout, float* const* dsegs, const int* C, const int* up, int nseg,
                     int B, int H, int W, int pad, void* stream) {
+  return fd_assemble_bwd2(dout, dsegs, nullptr, C, up, nseg, B, H, W, pad, stream);
+}
+
+int fd_assemble_bwd2(const float* dout, float* const* dsegs, float* const* dsegs2, const int* C, const int* up,
+                     int nseg, int B, int H, int W, int pad, void* stream) {
   AsmArgs a;
   int rc = fill_asm(a, nseg, C, up, B, H, W, pad);
   if (rc) return rc;
   for (int s = 0; s < nseg; ++s) {
-    if (!dsegs[s]) continue;
+    if (!dsegs[s]) {
+      FD_REQUIRE(!(dsegs2 && dsegs2[s]), "fd_assemble_bwd2: dsegs2[%d] without dsegs[%d]", s, s);
+      continue;
+    }
     a.d[s] = dsegs[s];
+    a.d2[s] = dsegs2 ? dsegs2[s] : nullptr;
     int u = up[s] ? 2 : 1;
     long npix = (long)B * (H / u) * (W / u);
-    bool v4 = npix * C[s] < (1L << 32) && a.Ctot % 4 == 0 && (((uintptr_t)dout | (uintptr_t)dsegs[s]) & 15) == 0;
+    bool v4 = npix * C[s] < (1L << 32) && a.Ctot % 4 == 0 &&
+              (((uintptr_t)dout | (uintptr_t)dsegs[s] | (uintptr_t)a.d2[s]) & 15) == 0;
     for (int i = 0; i <= s; ++i) v4 = v4 && C[i] % 4 == 0;      // this segment and its channel offset
     if (v4) {
       const unsigned total = (unsigned)(npix * (C[s] / 4));

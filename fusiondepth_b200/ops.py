@@ -59,9 +59,9 @@ STATS_ARENA: Optional[StatsArena] = None
 
 def zeroed_stats(n: int, device) -> torch.Tensor:
     """A zeroed float64 [n] buffer for fd_conv2d_fwd_tc_stats: a slice of the step's arena when one is active."""
-    # Opt-in (FD_STATS_ARENA=1): measured no faster than the per-call fills (504 vs 503-505 images/s), and one test
-    # order (the refiner tests before test_cuda_graph_replay_matches_eager) produced a 5 % gradient mismatch between
-    # graph replay and eager with it that the per-call buffers do not show -- not understood, so not the default.
+    # Opt-in (FD_STATS_ARENA=1): measured no faster than the per-call fills (504 vs 503-505 images/s).  (The 5 %
+    # graph-replay-vs-eager gradient mismatch once seen with it was the skip-connection gradient race described in
+    # AssembleFn.backward, which any change of timing could expose -- not the arena.)
     if STATS_ARENA is not None and os.environ.get("FD_STATS_ARENA", "0") == "1":
         t = STATS_ARENA.take(n)
         if t is not None:
@@ -253,6 +253,8 @@ def prep_input(x):
 # BatchNorm batch statistics out of the tensor-core convolution's epilogue instead of a separate pass over the
 # conv output (FD_BN_FUSE_STATS=0 restores the separate bn_stats kernel; both are parity-tested).
 FUSE_BN_STATS = os.environ.get("FD_BN_FUSE_STATS", "1") == "1"
+# BatchNorm + ReLU backward without the saved output (mask re-evaluated from x); FD_BN_XMASK=0 reads y back
+BN_XMASK = os.environ.get("FD_BN_XMASK", "1") == "1"
 
 
 def conv_emits_stats(Cin, Cout, has_bias) -> bool:
@@ -573,8 +575,11 @@ class BatchNormFn(torch.autograd.Function):
                                  _p(running_var), int(training), momentum, eps, int(relu), _p(y),
                                  _p(mean), _p(rstd), _p(ws), M, C, stat_weight, int(stats is not None),
                                  _stream()), "fd_bn_fwd")
-        ctx.save_for_backward(x, y, gamma, mean, rstd)
-        ctx.cfg = (int(relu), int(training), residual is not None)
+        # residual-free BatchNorm + ReLU in training: the backward rebuilds the ReLU mask from x (fd_bn_bwd_xmask)
+        # instead of reading y back -- beta is saved in its place
+        xmask = bool(BN_XMASK and relu and training and residual is None and lib.fd_bn_bwd_xmask_ok(M, C))
+        ctx.save_for_backward(x, beta if xmask else y, gamma, mean, rstd)
+        ctx.cfg = (int(relu), int(training), residual is not None, xmask)
         ctx.gg, ctx.gb = _direct_grad(gamma), _direct_grad(beta)
         return y
 
@@ -582,7 +587,7 @@ class BatchNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         lib = _lib.load()
         x, y, gamma, mean, rstd = ctx.saved_tensors
-        relu, training, has_res = ctx.cfg
+        relu, training, has_res, xmask = ctx.cfg
         dy = nhwc(dy)
         B, C, H, W = x.shape
         M = B * H * W
@@ -592,9 +597,14 @@ class BatchNormFn(torch.autograd.Function):
         dgamma = ctx.gg if direct else torch.empty(C, device=x.device, dtype=torch.float32)
         dbeta = ctx.gb if direct else torch.empty(C, device=x.device, dtype=torch.float32)
         ws = torch.empty(lib.fd_bn_workspace_bytes(C) // 8, device=x.device, dtype=torch.float64)
-        _lib.check(lib.fd_bn_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(mean), _p(rstd), relu, training,
-                                 _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, int(direct),
-                                 _stream()), "fd_bn_bwd")
+        if xmask:       # `y` holds beta
+            _lib.check(lib.fd_bn_bwd_xmask(_p(x), _p(dy), _p(gamma), _p(y), _p(mean), _p(rstd), training, _p(dx),
+                                           _p(dgamma), _p(dbeta), _p(ws), M, C, int(direct), _stream()),
+                       "fd_bn_bwd_xmask")
+        else:
+            _lib.check(lib.fd_bn_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(mean), _p(rstd), relu, training,
+                                     _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), M, C, int(direct),
+                                     _stream()), "fd_bn_bwd")
         if direct:
             return dx, None, None, None, None, dres, None, None, None, None, None, None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
@@ -678,27 +688,35 @@ class AssembleFn(torch.autograd.Function):
         pad, spec, Cs, B, H, W = ctx.cfg
         dout = nhwc(dout)
         n = len(spec)
-        ptrs = (c_void_p * n)()
+        ptrs, ptrs2 = (c_void_p * n)(), (c_void_p * n)()
         Carr = (c_int * n)(*Cs)
         uarr = (c_int * n)(*[int(u) for _, u in spec])
         grads: List[Optional[torch.Tensor]] = []
         need = ctx.needs_input_grad[2:]
         k = 0
-        dsegs = []
+        dsegs, dsegs2 = [], []
         for i, (has_b, up) in enumerate(spec):
             wants = need[k] or (has_b and need[k + 1])
             u = 2 if up else 1
             d = empty_nhwc(B, Cs[i], H // u, W // u, dout.device) if wants else None
+            # an `a + b` segment gets one gradient tensor PER operand, both written by the kernel.  The operands
+            # come from trunks on different streams; a single tensor handed to both lets the autograd engine
+            # accumulate the other contribution into it in place (use_count == 1 once the first consumer is done)
+            # on one stream while the other stream's kernels still read it -- nothing orders the two inside a
+            # captured graph (seen as an occasional wrong encoder gradient in graph replays)
+            d2 = empty_nhwc(B, Cs[i], H // u, W // u, dout.device) if (has_b and need[k] and need[k + 1]) else None
             ptrs[i] = d.data_ptr() if d is not None else None
+            ptrs2[i] = d2.data_ptr() if d2 is not None else None
             dsegs.append(d)
+            dsegs2.append(d2)
             k += 2 if has_b else 1
-        _lib.check(lib.fd_assemble_bwd(_p(dout), ptrs, Carr, uarr, n, B, H, W, pad, _stream()),
-                   "fd_assemble_bwd")
+        _lib.check(lib.fd_assemble_bwd2(_p(dout), ptrs, ptrs2, Carr, uarr, n, B, H, W, pad, _stream()),
+                   "fd_assemble_bwd2")
         k = 0
         for i, (has_b, up) in enumerate(spec):
             grads.append(dsegs[i] if need[k] else None)
             if has_b:
-                grads.append(dsegs[i] if need[k + 1] else None)
+                grads.append((dsegs2[i] if dsegs2[i] is not None else dsegs[i]) if need[k + 1] else None)
             k += 2 if has_b else 1
         return (None, None) + tuple(grads)
 
@@ -726,7 +744,8 @@ class AddFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g, g
+        # one tensor per operand: the operands' branches run on different streams (see AssembleFn.backward)
+        return g, (g.clone() if all(ctx.needs_input_grad) else g)
 
 
 def add(a, b):

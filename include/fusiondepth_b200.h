@@ -278,6 +278,14 @@ int fd_bn_bwd(const float* x, const float* y, const float* dy, const float* gamm
               const float* save_mean, const float* save_rstd, int relu, int training, float* dx,
               float* dresidual, float* dgamma, float* dbeta, double* ws, long M, int C,
               int accumulate_param_grads, void* stream);
+/* Backward of a residual-free BatchNorm + ReLU without the saved output: the ReLU mask y > 0 is re-evaluated
+ * from x, mean, rstd, gamma, beta with the forward's exact rounding (one tensor read less in each of the two
+ * passes).  gamma / beta must still hold the forward's values.  fd_bn_bwd_xmask_ok(M, C) == 0: tensor too small
+ * (single-kernel path of fd_bn_bwd), use fd_bn_bwd with y. */
+int fd_bn_bwd_xmask_ok(long M, int C);
+int fd_bn_bwd_xmask(const float* x, const float* dy, const float* gamma, const float* beta,
+                    const float* save_mean, const float* save_rstd, int training, float* dx, float* dgamma,
+                    float* dbeta, double* ws, long M, int C, int accumulate_param_grads, void* stream);
 
 /* nn.MaxPool2d(3, 2, 1)  (ResNet stem) */
 int fd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C,
@@ -299,6 +307,12 @@ int fd_assemble_fwd(const fd_segment* segs_host, int nseg, float* out, int B, in
 /* dseg[i] [B,Hs,Ws,C_i] = adjoint (gather form, deterministic) */
 int fd_assemble_bwd(const float* dout, float* const* dsegs_host, const int* C_host,
                     const int* up_host, int nseg, int B, int H, int W, int pad, void* stream);
+/* The same with an optional second destination per segment (dsegs2_host[i] nullable): the gradient of an `a + b`
+ * segment as two separate tensors, one per operand.  The operands of the skip connections live on different
+ * streams' autograd branches, and one tensor handed to both is open to the autograd engine accumulating into it in
+ * place on one stream while the other still reads it. */
+int fd_assemble_bwd2(const float* dout, float* const* dsegs_host, float* const* dsegs2_host, const int* C_host,
+                     const int* up_host, int nseg, int B, int H, int W, int pad, void* stream);
 
 int fd_add(const float* a, const float* b, float* out, long n, void* stream);
 /* out = relu(a + b): the residual join of a BasicBlock / Bottleneck whose BatchNorms are folded into the

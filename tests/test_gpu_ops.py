@@ -79,11 +79,41 @@ def test_conv2d_fwd_bwd(cuda, case):
         assert rel_err(bc.grad.cpu(), br.grad) < 5e-5
 
 
+@pytest.mark.parametrize("C", [64, 22])
+def test_batch_norm_backward_mask_from_x_is_bit_identical(cuda, C):
+    """fd_bn_bwd_xmask re-evaluates the ReLU mask from x; its gradients must equal the read-y-back path's bit for
+    bit (same kernels, same summation order, identical mask) -- including exact zeros of the affine output."""
+    from fusiondepth_b200 import ops
+    B, H, W = 6, 48, 40
+    x = _rand((B, C, H, W), 11) * 2 + 0.3
+    gamma, beta = 0.5 + torch.rand(C, generator=torch.Generator().manual_seed(12)), _rand((C,), 13, 0.2)
+    gamma[1] = 0.0
+    beta[1] = 0.0          # channel 1: affine output exactly 0 everywhere -> mask all-false on both paths
+    gy = _rand((B, C, H, W), 14)
+    res = {}
+    for flag in (True, False):
+        ops.BN_XMASK = flag
+        try:
+            xc = x.cuda().contiguous(memory_format=CL).requires_grad_(True)
+            gc, bc = gamma.cuda().requires_grad_(True), beta.cuda().requires_grad_(True)
+            rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+            yc = ops.batch_norm(xc, gc, bc, rm, rv, None, True, 0.1, 1e-5, True)
+            yc.backward(gy.cuda().contiguous(memory_format=CL))
+            res[flag] = (yc.detach().clone(), xc.grad.clone(), gc.grad.clone(), bc.grad.clone())
+        finally:
+            ops.BN_XMASK = True
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)
+    assert float(res[True][1].abs().sum()) > 0
+
+
 @pytest.mark.parametrize("C,relu,res,training,hw", [
     (64, True, False, True, (10, 14)), (128, True, True, True, (10, 14)), (20, False, False, True, (10, 14)),
     (64, True, True, False, (10, 14)),
     # M = 3*40*48 = 5760 > 1024 rows: the multi-kernel path (fp64 atomics); M = 420: one fused kernel
-    (64, True, True, True, (40, 48)), (32, False, False, True, (40, 48))])
+    (64, True, True, True, (40, 48)), (32, False, False, True, (40, 48)),
+    # residual-free BatchNorm + ReLU on the multi-kernel path: the backward rebuilds the mask from x (fd_bn_bwd_xmask)
+    (64, True, False, True, (40, 48)), (22, True, False, True, (40, 48))])
 def test_batch_norm(cuda, C, relu, res, training, hw):
     from fusiondepth_b200 import ops
     B, (H, W) = 3, hw

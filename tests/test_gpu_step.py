@@ -202,6 +202,39 @@ def test_cuda_graph_replay_matches_eager(cuda):
     assert float((w_graph - step.flat.data)[big].abs().max()) <= 0.05 * step.lr
 
 
+def test_cuda_graph_replays_are_stable(cuda):
+    """Every replay of the captured step must give the eager step's gradients.  The graph's stream branches really
+    run concurrently, so a missing dependency shows up as an occasional wrong replay: the skip connections'
+    gradient used to be ONE tensor handed to the encoder (main stream) and the beam encoder (side stream), and the
+    autograd engine's in-place accumulation into it on one stream raced the other stream's read -- about one
+    replay in twelve came back with the encoder's gradients off by 10-100 %."""
+    from fusiondepth_b200 import training
+    torch.manual_seed(0)
+    models = training.build_models(18, "cuda")
+    _load(models, 5)
+    batches = [synth.to_device(synth.make_batch(2, 64, 96, seed=20, with_noise=False), "cuda")]
+    noises = [{s: torch.randn(2, 2, 64, 96, device="cuda") for s in range(4)}]
+    step = training.TrainStep(models, lr=1e-4, accumulate=1)
+    step.capture(batches, noises)
+    w0 = step.flat.data.clone()
+    bn0 = step._bn_state()
+
+    def reset():
+        step.flat.data.copy_(w0)
+        step._bn_state(bn0)
+        step.exp_avg.zero_(); step.exp_avg_sq.zero_(); step.adam_state[:3].zero_()
+
+    reset()
+    step.step(batches, noises)
+    g_eager = step.flat.grad.clone()
+    worst = 0.0
+    for _ in range(24):
+        reset()
+        step.replay()
+        worst = max(worst, rel_err(step.flat.grad, g_eager))
+    assert worst < 2e-3, worst
+
+
 def test_abs_rel_matches_reference_disparities(cuda):
     """evaluate_depth.py's AbsRel (evaluate_depth.py:42-60, 344-378: bilinear resize to the ground-truth
     size, Garg crop, per-image median scaling, clip to [1e-3, 80]) of OUR eval-mode disparities against
