@@ -1,6 +1,7 @@
 """Diagnostic (not a test): per-parameter difference between the captured-graph step's gradients and the eager
 step's, on the small problem of tests/test_gpu_step.py::test_cuda_graph_replay_matches_eager.
-usage: python tools/diag_graph_eager.py [n_repeats] [serial] [nodirect] [nocache]"""
+usage: python tools/diag_graph_eager.py [n_repeats] [serial] [nodirect] [nocache] [full]
+(full: the bench configuration, 2 micro-batches of 6 x 192 x 640)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,10 +12,11 @@ from tests.test_gpu_step import _load
 torch.manual_seed(0)
 models = training.build_models(18, "cuda")
 _load(models, 5)
-batches = [synth.to_device(synth.make_batch(2, 64, 96, seed=20, with_noise=False), "cuda")]
-noises = [{s: torch.randn(2, 2, 64, 96, device="cuda") for s in range(4)}]
 flags = sys.argv[2:]
-step = training.TrainStep(models, lr=1e-4, accumulate=1, parallel_trunks="serial" not in flags,
+NB, (B, H, W) = (2, (6, 192, 640)) if "full" in flags else (1, (2, 64, 96))
+batches = [synth.to_device(synth.make_batch(B, H, W, seed=20 + i, with_noise=False), "cuda") for i in range(NB)]
+noises = [{s: torch.randn(B, 2, H, W, device="cuda") for s in range(4)} for i in range(NB)]
+step = training.TrainStep(models, lr=1e-4, accumulate=NB, parallel_trunks="serial" not in flags,
                           direct_grad="nodirect" not in flags, cache_weight_prep="nocache" not in flags)
 print("flags", flags)
 step.capture(batches, noises)
