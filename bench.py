@@ -290,23 +290,36 @@ def ncu_traffic(which="conv"):
 def dominant_kernel_leg(dev):
     """The most frequent tensor-core conv of the step (ResNet layer1 3x3 64->64 on 6x48x160, 112 of
     the ~390 forward / data-gradient conv launches per step are this shape): average launch duration
-    over 3 x 20 back-to-back launches captured in a CUDA graph, CUDA events, inputs L2-warm."""
-    from fusiondepth_b200 import ops
-    CL = torch.channels_last
+    over 3 x 20 back-to-back launches captured in a CUDA graph, CUDA events, inputs L2-warm.  The kernel is
+    launched through the C-ABI entry point the step uses (fd_conv2d_fwd_tc) with the low-order weight tensor
+    prepared once, as the step's weight cache does -- ops.conv2d without that cache would add one fd_tf32_split
+    launch per call to the timed region."""
+    import ctypes
+    from fusiondepth_b200 import _lib
+    lib = _lib.load()
     B, C, H, W = MICRO_B, 64, globals()["H"] // 4, globals()["W"] // 4
-    x = torch.randn(B, C, H, W, device=dev).contiguous(memory_format=CL)
-    w = torch.randn(C, C, 3, 3, device=dev).contiguous(memory_format=CL)
+    x = torch.randn(B, H, W, C, device=dev)                       # NHWC
+    w = torch.randn(C, 3, 3, C, device=dev)                       # [Cout, KH, KW, Cin]
+    wlo = torch.empty_like(w)
+    y = torch.empty(B, H, W, C, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
-    with torch.no_grad():
-        with torch.cuda.stream(s):
-            ops.conv2d(x, w, None, 1, 1, "none")
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(20):
-                ops.conv2d(x, w, None, 1, 1, "none")
+
+    def launch():
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.fd_conv2d_fwd_tc(P(x), P(w), P(wlo), None, P(y), B, H, W, C, C, 3, 3, 1, 1, 0, st),
+                   "fd_conv2d_fwd_tc")
+
+    with torch.cuda.stream(s):
+        _lib.check(lib.fd_tf32_split(P(w), P(wlo), w.numel(), ctypes.c_void_p(s.cuda_stream)), "fd_tf32_split")
+        launch()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(20):
+            launch()
     g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -122,7 +122,12 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool ktrace = a.trace && blockIdx.x == 0;
-  if (ktrace && tid == 0) a.trace[3 * T4_TRACE_KB * 4 + 0] = clock64();
+  if (ktrace && tid == 0) {
+    a.trace[3 * T4_TRACE_KB * 4 + 0] = clock64();
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[3 * T4_TRACE_KB * 4 + 5] = gt;                  // wall-clock ns: launch-to-launch gaps, SM clock rate
+  }
   // Tiles never cross an image (see conv_tc3.cu).  Tile id T -> (m tile x, n tile y), x fastest.
   const int HoWo = a.Ho * a.Wo;
   const int tpi = (HoWo + BM - 1) / BM;
@@ -546,7 +551,12 @@ conv_tc4_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (ktrace && tid == 0) a.trace[3 * T4_TRACE_KB * 4 + 4] = clock64();
+  if (ktrace && tid == 0) {
+    a.trace[3 * T4_TRACE_KB * 4 + 4] = clock64();
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[3 * T4_TRACE_KB * 4 + 6] = gt;
+  }
   if (warp == C::MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
