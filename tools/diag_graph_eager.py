@@ -1,6 +1,6 @@
 """Diagnostic (not a test): per-parameter difference between the captured-graph step's gradients and the eager
 step's, on the small problem of tests/test_gpu_step.py::test_cuda_graph_replay_matches_eager.
-usage: python tools/diag_graph_eager.py [n_repeats] [serial] [nodirect] [nocache] [full]
+usage: python tools/diag_graph_eager.py [n_repeats] [serial] [nodirect] [nocache] [full] [mb2] [mid]
 (full: the bench configuration, 2 micro-batches of 6 x 192 x 640)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,6 +14,10 @@ models = training.build_models(18, "cuda")
 _load(models, 5)
 flags = sys.argv[2:]
 NB, (B, H, W) = (2, (6, 192, 640)) if "full" in flags else (1, (2, 64, 96))
+if "mb2" in flags:          # two concurrent micro-batches of the small problem
+    NB = 2
+if "mid" in flags:
+    B, H, W = 3, 96, 160
 batches = [synth.to_device(synth.make_batch(B, H, W, seed=20 + i, with_noise=False), "cuda") for i in range(NB)]
 noises = [{s: torch.randn(B, 2, H, W, device="cuda") for s in range(4)} for i in range(NB)]
 step = training.TrainStep(models, lr=1e-4, accumulate=NB, parallel_trunks="serial" not in flags,
