@@ -190,6 +190,12 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     mbar_init(turn_bar(0), 1);
     mbar_init(turn_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // Prologue breakdown (tools/trace_conv3.py): this serial initialisation ends at ~1400-1500 clk, the row table at
+    // ~1100, the tensor-memory allocation at ~500.  Spreading the list over two warps (one barrier per thread) brought
+    // the __syncthreads from ~1650 to ~1270 clk but made the persistent layer-1 kernel and the step SLOWER
+    // (29.05 vs 28.4 us, 500 vs 508 images/s: the extra warps walking the list compete with the first loads), and
+    // over all warps it cost 600 clk more than it saved -- measured, reverted.
+    if (ktrace) a.trace[3 * T3_TRACE_KB * 4 + 5] = clock64();          // barriers initialised
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
   }
@@ -197,7 +203,9 @@ conv_tc3_kernel(TcArgs a, const __grid_constant__ CUtensorMap tm_w, const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (ktrace && lane == 0) a.trace[3 * T3_TRACE_KB * 4 + 6] = clock64();   // tensor memory allocated
   }
+  if (ktrace && tid == 127) a.trace[3 * T3_TRACE_KB * 4 + 7] = clock64();    // row table written (last table thread)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -22,13 +22,15 @@ for B, Cin, H, W, Cout in [(6, 64, 48, 160, 64), (6, 128, 24, 80, 128), (6, 512,
         torch.cuda.synchronize()
         lib.fd_debug_set_conv_trace(None)
     t = trace.cpu()
-    ph = t[3 * KB * 4:3 * KB * 4 + 5].tolist()
+    ph = t[3 * KB * 4:3 * KB * 4 + 8].tolist()
     nk = Cin * 9 // 32
     r = t[:3 * KB * 4].view(3, KB, 4)[:, :nk]
     t0 = ph[0]
     print("shape", (B, Cin, H, W, Cout), "nk", nk)
     print("  kernel phases (clk since CTA start): prologue done %d, epilogue start %d, epilogue done %d, exit barrier %d"
           % (ph[1] - t0, ph[2] - t0, ph[3] - t0, ph[4] - t0))
+    print("  inside the prologue: barriers initialised %d, tensor memory allocated %d, row table written %d"
+          % (ph[5] - t0, ph[6] - t0, ph[7] - t0))
     names = ["A split g0 [start, loaded+split, post tfree wait, arrived]", "mma        [start, post wready, post tfull, issued]",
              "W path     [TMA warp at kb, stage free -> TMA issued, landed (splitter woke), W_lo ready]"]
     show = list(range(0, min(nk, 12))) + list(range(max(12, nk - 4), nk))
