@@ -190,13 +190,15 @@ def test_cuda_graph_replay_matches_eager(cuda):
     assert abs(l_graph - l_eager) < 1e-5 * abs(l_eager)
     # the flat gradient buffers themselves (fp32 atomics: summation order varies run to run)
     assert float(g_eager.abs().max()) > 0
-    assert rel_err(g_graph.cpu(), g_eager.cpu()) < 5e-4
+    # run-to-run spread is ~1.5e-4 (one arg-min / ReLU flip shows as ~8e-4); a missing dependency between the
+    # graph's branches shows as 5e-2 and more (test_cuda_graph_replays_are_stable)
+    assert rel_err(g_graph.cpu(), g_eager.cpu()) < 2e-3
     # per parameter, so that small-gradient tensors are checked at their own scale
     for p in step.flat.params[::7]:
         off, k = step.flat.offsets[p], p.numel()
         a, b = g_graph[off:off + k], g_eager[off:off + k]
         if float(b.abs().max()) > 0:
-            assert rel_err(a.cpu(), b.cpu()) < 2e-3
+            assert rel_err(a.cpu(), b.cpu()) < 5e-3
     # Adam's first update is lr * g / (|g| + eps): identical gradients give identical weights
     big = g_eager.abs() > 1e-3 * g_eager.abs().max()
     assert float((w_graph - step.flat.data)[big].abs().max()) <= 0.05 * step.lr
