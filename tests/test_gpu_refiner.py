@@ -15,8 +15,11 @@ pytestmark = pytest.mark.gpu
 def _gtol(key):
     """Gradient-norm tolerance.  The biases of the four 1-channel disparity heads get the plain SUM of
     dL/dlogit over all pixels -- signed terms that cancel to ~1e-3 of their absolute sum -- so fp32
-    summation-order differences of 1e-6 show up as ~1 % there; every other tensor holds 5e-3."""
-    return 2e-2 if key.endswith("conv.bias") and key.split(".")[1] in ("10", "11", "12", "13") else 5e-3
+    summation-order differences of 1e-6 show up as ~1 % there.  Their weights see the si-loss term of their scale
+    directly, and that term averages over the few LiDAR points passing `|depth - beam| < thresh`: one point at the
+    threshold flipping (fp32 rounding; varies run to run with the atomics upstream) moved decoder.12.conv.weight's
+    norm by 0.8 % in one of five runs.  Heads: 2e-2; every other tensor holds 5e-3."""
+    return 2e-2 if key.split(".")[1] in ("10", "11", "12", "13") and ".conv." in key else 5e-3
 
 
 def _load(models, seed):
